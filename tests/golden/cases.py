@@ -1,0 +1,60 @@
+"""Shared definitions of the golden cases: the INPUTS, regenerated deterministically.
+
+Imported by ``make_golden.py`` (which runs the reference on them, in the build
+container) and by the tests (which run the oracle / the CUDA path on the same inputs,
+anywhere).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import evennicer_slam_b200.synthetic as syn
+
+SEED = 20                      # run.py:11-20 -- the authors' own setup_seed(20)
+N_TINY_RAYS = 96
+N_ROOM0_RAYS = 1000
+TINY_STD = {"coarse": 0.05, "middle": 0.05, "fine": 0.05, "color": 0.05}
+
+
+def tiny_scene():
+    return syn.make_scene(syn.TINY_BOUND, syn.TINY_CAM, seed=SEED, name="tiny", grid_std=TINY_STD)
+
+
+def tiny_frame():
+    cam_t = syn.default_pose(syn.TINY_BOUND, jitter_seed=1)
+    depth, color, event = syn.synthetic_frame(syn.TINY_BOUND, syn.TINY_CAM, cam_t, seed=SEED,
+                                              zero_frac=0.1)
+    return cam_t, depth, color, event
+
+
+def room0_scene():
+    return syn.make_scene(syn.ROOM0_BOUND, syn.REPLICA_CAM, seed=SEED, name="room0",
+                          grid_std={"fine": 0.01})
+
+
+def room0_frame():
+    cam_t = syn.default_pose(syn.ROOM0_BOUND, jitter_seed=2)
+    depth, color, event = syn.synthetic_frame(syn.ROOM0_BOUND, syn.REPLICA_CAM, cam_t, seed=SEED,
+                                              zero_frac=0.02)
+    return cam_t, depth, color, event
+
+
+def upstream_grads(n: int):
+    """Deterministic dL/d(depth, var, color) so every output path carries gradient."""
+    g_d = syn.det_uniform((n,), 301) * 2.0 - 1.0
+    g_v = syn.det_uniform((n,), 302) * 2.0 - 1.0
+    g_c = (syn.det_uniform((n, 3), 303) * 2.0 - 1.0).astype(np.float32)
+    return g_d, g_v, g_c
+
+
+def eval_points_lattice(scene, n_per_axis=(9, 8, 7), margin=0.25):
+    """float64 points on a lattice that overshoots the bound (exercises the =100 rule,
+    border clamping and the enlarged coarse bound)."""
+    b = scene.bound
+    axes = [np.linspace(b[k, 0] - margin, b[k, 1] + margin, n_per_axis[k]) for k in range(3)]
+    xx, yy, zz = np.meshgrid(*axes, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], -1)
+    # a few points exactly on the bound faces / voxel centres
+    extra = np.array([[b[0, 0], b[1, 0], b[2, 0]], [b[0, 1], b[1, 1], b[2, 1]],
+                      [b[0, 0], 0.0, 0.0], [0.0, b[1, 1], 0.0], [0.0, 0.0, 0.0]])
+    return np.ascontiguousarray(np.concatenate([pts, extra], 0))

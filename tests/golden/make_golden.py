@@ -1,0 +1,197 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE.
+
+Run in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+The reference's own code (src/common.py, src/conv_onet/models/decoder.py,
+src/utils/Renderer.py -- imported from /root/reference with the two CPU shims of
+``ref_harness.py``) produces every array saved here; the inputs are regenerated
+deterministically from ``evennicer_slam_b200.synthetic`` by the tests, so only
+outputs are stored.  torch CPU, float32/float64 exactly as the reference runs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_harness as rh                                   # noqa: E402
+import evennicer_slam_b200.synthetic as syn                # noqa: E402
+from cases import (TINY_STD, tiny_scene, tiny_frame, upstream_grads, eval_points_lattice,     # noqa: E402
+                   room0_scene, room0_frame, N_TINY_RAYS, N_ROOM0_RAYS, SEED)
+
+STAGES = ("coarse", "middle", "fine", "color")
+
+
+def t_vals_np():
+    return (torch.linspace(0., 1., steps=32).numpy(),
+            torch.linspace(0., 1., steps=16).double().numpy())
+
+
+def run_render_case(ref, model, c, renderer, cam, cam_t, depth, color, n, stage, use_depth,
+                    crop=None):
+    """get_samples -> render_batch_ray -> weighted-sum loss -> backward, all reference code."""
+    torch.manual_seed(SEED)
+    for p in model.parameters():
+        p.grad = None
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    ct = torch.from_numpy(cam_t.copy()).requires_grad_(True)
+    c2w = ref.common.get_camera_from_tensor(ct)
+    H0, H1, W0, W1 = crop if crop else (0, cam.H, 0, cam.W)
+    ro, rd, sd, scol = ref.common.get_samples(H0, H1, W0, W1, n, cam.H, cam.W, cam.fx, cam.fy,
+                                              cam.cx, cam.cy, c2w, torch.from_numpy(depth),
+                                              torch.from_numpy(color), "cpu")
+    ro.retain_grad()
+    rd.retain_grad()
+    d, u, col = renderer.render_batch_ray(cg, model, rd, ro, "cpu", stage,
+                                          gt_depth=sd if use_depth else None)
+    g_d, g_v, g_c = upstream_grads(n)
+    loss = (d * torch.from_numpy(g_d)).sum() + (u * torch.from_numpy(g_v)).sum() \
+        + (col.double() * torch.from_numpy(g_c).double()).sum()
+    loss.backward()
+    out = dict(rays_o=ro.detach().numpy(), rays_d=rd.detach().numpy(), sample_depth=sd.numpy(),
+               sample_color=scol.numpy(), depth=d.detach().numpy(), var=u.detach().numpy(),
+               color=col.detach().numpy(), g_rays_o=ro.grad.numpy(), g_rays_d=rd.grad.numpy(),
+               g_cam=ct.grad.numpy(), c2w=c2w.detach().numpy())
+    for lv in STAGES:
+        dec = getattr(model, lv + "_decoder")
+        for k, p in dec.named_parameters():
+            if p.grad is not None:
+                out[f"gdec.{lv}.{k}"] = p.grad.numpy().copy()
+    for k, v in cg.items():
+        if v.grad is not None:
+            out["ggrid." + k] = v.grad.numpy().copy()
+    return out
+
+
+def recompute_indices(n, cam, crop=None):
+    torch.manual_seed(SEED)
+    H0, H1, W0, W1 = crop if crop else (0, cam.H, 0, cam.W)
+    return torch.randint((H1 - H0) * (W1 - W0), (n,)).numpy()
+
+
+def main():
+    ref = rh.load()
+    import src.utils.Renderer as RM
+    t32, t64 = t_vals_np()
+    saved = {}
+
+    # ---------------- tiny scene: every stage x {gt_depth, None}, full tensors -------------
+    scene = tiny_scene()
+    model, c, renderer, cfg = rh.build_reference(scene)
+    cam_t, depth, color, event = tiny_frame()
+    cam = scene.cam
+    captured = {}
+    orig = RM.raw2outputs_nerf_color
+
+    def spy(raw, z_vals, rays_d, occupancy=False, device="cpu"):
+        captured["z"] = z_vals.detach().numpy().copy()
+        captured["raw"] = raw.detach().numpy().copy()          # before the in-place sigmoid
+        return orig(raw, z_vals, rays_d, occupancy=occupancy, device=device)
+    RM.raw2outputs_nerf_color = spy
+
+    tiny = {}
+    tiny["indices"] = recompute_indices(N_TINY_RAYS, cam)
+    for stage in STAGES:
+        for use_depth in (True, False):
+            out = run_render_case(ref, model, c, renderer, cam, cam_t, depth, color,
+                                  N_TINY_RAYS, stage, use_depth)
+            out["z_vals"] = captured["z"]
+            out["raw"] = captured["raw"]
+            tag = f"{stage}.{'d' if use_depth else 'n'}"
+            for k, v in out.items():
+                tiny[f"{tag}.{k}"] = v
+            print("tiny", tag, "depth mean", out["depth"].mean(), "sum w-ish", out["color"].mean())
+    np.savez_compressed(os.path.join(HERE, "tiny_render.npz"), **tiny)
+
+    # ---------------- tiny scene: eval_points (f64 points incl. out-of-bound) --------------
+    ev = {}
+    pts = eval_points_lattice(scene)
+    for stage in STAGES:
+        with torch.no_grad():
+            r = renderer.eval_points(torch.from_numpy(pts.copy()), model, c, stage, "cpu")
+        ev[f"{stage}.f64"] = r.numpy()
+        with torch.no_grad():
+            r32 = renderer.eval_points(torch.from_numpy(pts.astype(np.float32)), model, c, stage, "cpu")
+        ev[f"{stage}.f32"] = r32.numpy()
+    np.savez_compressed(os.path.join(HERE, "tiny_eval_points.npz"), **ev)
+
+    # ---------------- tiny scene: full-frame lattices (get_rays / get_rays_rescale) ---------
+    fr = {}
+    ct = torch.from_numpy(cam_t.copy()).requires_grad_(True)
+    c2w = ref.common.get_camera_from_tensor(ct)
+    ro, rd = ref.common.get_rays(cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w, "cpu")
+    fr["full.rays_o"] = ro.detach().numpy()
+    fr["full.rays_d"] = rd.detach().numpy()
+    nH, nW = int(cam.H * 0.5), int(cam.W * 0.5)
+    ro2, rd2 = ref.common.get_rays_rescale(cam.H, cam.W, nH, nW, cam.fx, cam.fy, cam.cx, cam.cy,
+                                           c2w, "cpu")
+    fr["rescale.rays_o"] = ro2.detach().numpy()
+    fr["rescale.rays_d"] = rd2.detach().numpy()
+    gsum = torch.from_numpy(syn.det_uniform((nH, nW, 3), 555).astype(np.float32))
+    ((rd2 * gsum).sum() + (ro2 * gsum * 0.5).sum()).backward()
+    fr["rescale.g_cam"] = ct.grad.numpy().copy()
+    # render_img / render_img_rescale (no_grad full frame; with-grad rescaled frame)
+    with torch.no_grad():
+        d, u, col = renderer.render_img(c, model, c2w.detach(), "cpu", "color",
+                                        gt_depth=torch.from_numpy(depth))
+    fr["render_img.depth"] = d.numpy()
+    fr["render_img.var"] = u.numpy()
+    fr["render_img.color"] = col.numpy()
+    ct2 = torch.from_numpy(cam_t.copy()).requires_grad_(True)
+    c2w2 = ref.common.get_camera_from_tensor(ct2)
+    d, u, col = renderer.render_img_rescale(c, model, c2w2, "cpu", "color",
+                                            gt_depth=torch.from_numpy(depth), scale_factor=0.5)
+    fr["render_img_rescale.depth"] = d.detach().numpy()
+    fr["render_img_rescale.color"] = col.detach().numpy()
+    (col * gsum).sum().backward()
+    fr["render_img_rescale.g_cam"] = ct2.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "tiny_frames.npz"), **fr)
+
+    # ---------------- room0: 1000-ray colour-stage mapping batch (config C1) ---------------
+    scene = room0_scene()
+    model, c, renderer, cfg = rh.build_reference(scene)
+    cam_t, depth, color, event = room0_frame()
+    cam = scene.cam
+    out = run_render_case(ref, model, c, renderer, cam, cam_t, depth, color, N_ROOM0_RAYS,
+                          "color", True)
+    room = {"indices": recompute_indices(N_ROOM0_RAYS, cam), "z_vals": captured["z"]}
+    for k, v in out.items():
+        if k.startswith("ggrid."):
+            flat = v.reshape(-1)
+            nz = np.flatnonzero(flat)
+            probe = nz[:: max(1, len(nz) // 8192)][:8192]
+            room[k + ".nnz"] = np.int64(len(nz))
+            room[k + ".sum"] = np.float64(flat.astype(np.float64).sum())
+            room[k + ".l1"] = np.float64(np.abs(flat.astype(np.float64)).sum())
+            room[k + ".probe_idx"] = probe
+            room[k + ".probe_val"] = flat[probe]
+        else:
+            room[k] = v
+    # tracker crop variant (config C2 pixel draw): indices + rays only
+    crop = (100, cam.H - 100, 100, cam.W - 100)
+    room["crop.indices"] = recompute_indices(200, cam, crop)
+    torch.manual_seed(SEED)
+    ro, rd, sd, scol = ref.common.get_samples(*crop, 200, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy,
+                                              torch.from_numpy(out["c2w"]), torch.from_numpy(depth),
+                                              torch.from_numpy(color), "cpu")
+    room["crop.rays_d"] = rd.numpy()
+    room["crop.sample_depth"] = sd.numpy()
+    room["crop.sample_color"] = scol.numpy()
+    np.savez_compressed(os.path.join(HERE, "room0_color_1000.npz"), **room)
+    RM.raw2outputs_nerf_color = orig
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
