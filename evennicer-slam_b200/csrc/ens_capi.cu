@@ -1,0 +1,29 @@
+// Version / error strings / size queries of the C ABI (include/ens_render.h).
+#include "ens_common.cuh"
+
+extern "C" int ens_version(void) { return ENS_ABI_VERSION; }
+
+extern "C" const char *ens_strerror(int code) {
+  switch (code) {
+    case ENS_OK: return "ok";
+    case ENS_EINVAL: return "invalid argument (null pointer, bad enum or negative size)";
+    case ENS_ESHAPE: return "inconsistent shape or size";
+    case ENS_ECUDA: return "CUDA error (see cudaGetLastError)";
+    case ENS_ENCCL: return "collective error";
+    case ENS_EUNSUPPORTED: return "unsupported rendering mode (N_importance>0, occupancy=False, perturb>0 or lindisp)";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int64_t ens_packed_decoder_floats(int level) {
+  if (level < 0 || level > 3) return -1;
+  return ens::packed_floats(level);
+}
+extern "C" int64_t ens_decoder_grad_floats(int level) {
+  if (level < 0 || level > 3) return -1;
+  return ens::grad_floats(level);
+}
+extern "C" int ens_decoder_num_tensors(int level) {
+  if (level < 0 || level > 3) return -1;
+  return level == ENS_LEVEL_COARSE ? 12 : 23;
+}

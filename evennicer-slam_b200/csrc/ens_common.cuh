@@ -1,0 +1,158 @@
+// Shared device/host definitions for the fused renderer (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ens_render.h"
+
+#define ENS_CHECK_CUDA()                                   \
+  do {                                                     \
+    cudaError_t e__ = cudaPeekAtLastError();               \
+    if (e__ != cudaSuccess) return ENS_ECUDA;              \
+  } while (0)
+
+namespace ens {
+
+constexpr int C = 32;      // feature channels per grid level
+constexpr int HID = 32;    // hidden width of every decoder
+constexpr int EMB = 93;    // Fourier features
+constexpr int EMBP = 96;   // EMB padded to a multiple of 4 for the packed _B rows
+
+// ---------------------------------------------------------------------------------------------
+// Packed decoder blob (what the kernels stage into shared memory).  All matrices are stored
+// TRANSPOSED, [in][out=32], so the 32 output weights of one input feature are one 128-byte row.
+//   MLP (middle / fine / color), CD = c_dim (32 | 64):
+//     B      [3][96]                      (Fourier matrix, k padded with zeros)
+//     layer i=0..4:  W_iT [K_i][32], b_i [32], Wc_iT [CD][32], bc_i [32]     K = {93,32,32,125,32}
+//     out:   WoT [32][4], bo [4]          (1-output decoders use column 0; the rest is zero)
+//   MLP_no_xyz (coarse):
+//     layer i=0..4:  W_iT [K_i][32], b_i [32]                               K = {32,32,32,64,32}
+//     out:   WoT [32][4], bo [4]
+// Layer 3's input is the skip concat: MLP rows 0..92 = embedding, 93..124 = h2 (decoder.py:198-199);
+// MLP_no_xyz rows 0..31 = c, 32..63 = h2 (decoder.py:271-272).
+// ---------------------------------------------------------------------------------------------
+template <int CD>
+struct MlpPack {
+  __host__ __device__ static constexpr int K(int i) { return i == 0 ? 93 : (i == 3 ? 125 : 32); }
+  __host__ __device__ static constexpr int layer_floats(int i) { return K(i) * 32 + 32 + CD * 32 + 32; }
+  __host__ __device__ static constexpr int off_B() { return 0; }
+  __host__ __device__ static constexpr int off_layer(int i) {
+    int o = 3 * EMBP;
+    for (int t = 0; t < i; ++t) o += layer_floats(t);
+    return o;
+  }
+  __host__ __device__ static constexpr int off_W(int i) { return off_layer(i); }
+  __host__ __device__ static constexpr int off_b(int i) { return off_layer(i) + K(i) * 32; }
+  __host__ __device__ static constexpr int off_Wc(int i) { return off_b(i) + 32; }
+  __host__ __device__ static constexpr int off_bc(int i) { return off_Wc(i) + CD * 32; }
+  __host__ __device__ static constexpr int off_Wo() { return off_layer(5); }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int total() { return off_bo() + 4; }
+};
+
+struct CoarsePack {
+  __host__ __device__ static constexpr int K(int i) { return i == 3 ? 64 : 32; }
+  __host__ __device__ static constexpr int off_W(int i) {
+    int o = 0;
+    for (int t = 0; t < i; ++t) o += K(t) * 32 + 32;
+    return o;
+  }
+  __host__ __device__ static constexpr int off_b(int i) { return off_W(i) + K(i) * 32; }
+  __host__ __device__ static constexpr int off_Wo() { return off_W(5); }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int total() { return off_bo() + 4; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Flat gradient buffer of one decoder = its tensors back to back in state_dict order, reference
+// shapes (decoder.py:118-150):  fc_c.i.{weight [32][CD], bias [32]} i=0..4, embedder._B [3][93],
+// pts_linears.i.{weight [32][K_i], bias [32]} i=0..4, output_linear.{weight [NO][32], bias [NO]}.
+// ---------------------------------------------------------------------------------------------
+template <int CD, int NO>
+struct MlpGrad {
+  __host__ __device__ static constexpr int K(int i) { return MlpPack<CD>::K(i); }
+  __host__ __device__ static constexpr int off_Wc(int i) { return i * (32 * CD + 32); }
+  __host__ __device__ static constexpr int off_bc(int i) { return off_Wc(i) + 32 * CD; }
+  __host__ __device__ static constexpr int off_B() { return 5 * (32 * CD + 32); }
+  __host__ __device__ static constexpr int off_W(int i) {
+    int o = off_B() + 3 * EMB;
+    for (int t = 0; t < i; ++t) o += 32 * K(t) + 32;
+    return o;
+  }
+  __host__ __device__ static constexpr int off_b(int i) { return off_W(i) + 32 * K(i); }
+  __host__ __device__ static constexpr int off_Wo() { return off_W(5); }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + NO * 32; }
+  __host__ __device__ static constexpr int total() { return off_bo() + NO; }
+};
+
+struct CoarseGrad {
+  __host__ __device__ static constexpr int K(int i) { return CoarsePack::K(i); }
+  __host__ __device__ static constexpr int off_W(int i) {
+    int o = 0;
+    for (int t = 0; t < i; ++t) o += 32 * K(t) + 32;
+    return o;
+  }
+  __host__ __device__ static constexpr int off_b(int i) { return off_W(i) + 32 * K(i); }
+  __host__ __device__ static constexpr int off_Wo() { return off_W(5); }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 32; }
+  __host__ __device__ static constexpr int total() { return off_bo() + 1; }
+};
+
+__host__ __device__ inline int packed_floats(int level) {
+  switch (level) {
+    case ENS_LEVEL_COARSE: return CoarsePack::total();
+    case ENS_LEVEL_FINE: return MlpPack<64>::total();
+    default: return MlpPack<32>::total();
+  }
+}
+__host__ __device__ inline int grad_floats(int level) {
+  switch (level) {
+    case ENS_LEVEL_COARSE: return CoarseGrad::total();
+    case ENS_LEVEL_MIDDLE: return MlpGrad<32, 1>::total();
+    case ENS_LEVEL_FINE: return MlpGrad<64, 1>::total();
+    default: return MlpGrad<32, 4>::total();
+  }
+}
+
+// Scene as the kernels see it (passed by value as a kernel parameter).
+struct DevScene {
+  const float *grid[4];
+  int dims[4][3];        // Z,Y,X
+  double lo[3], hi[3];   // slam.bound
+  double clo[3], chi[3]; // coarse bound
+  const float *w[4];
+};
+
+inline DevScene make_dev_scene(const EnsScene *s) {
+  DevScene d;
+  for (int l = 0; l < 4; ++l) {
+    d.grid[l] = s->grid[l];
+    d.w[l] = s->weights[l];
+    for (int k = 0; k < 3; ++k) d.dims[l][k] = s->dims[l][k];
+  }
+  for (int k = 0; k < 3; ++k) {
+    d.lo[k] = s->bound[k][0];
+    d.hi[k] = s->bound[k][1];
+    d.clo[k] = s->coarse_bound[k][0];
+    d.chi[k] = s->coarse_bound[k][1];
+  }
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tmax_nan(double a, double b) {  // torch.max: NaN-propagating
+  return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+}
+__device__ __forceinline__ double tmin_nan(double a, double b) {
+  return (a != a) ? a : ((b != b) ? b : (a < b ? a : b));
+}
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  // vectorised no-return global reduction (sm_90+): one 16-byte L2 atomic instead of four
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+}  // namespace ens

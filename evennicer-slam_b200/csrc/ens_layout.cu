@@ -1,0 +1,212 @@
+// Layout plumbing: grid layout conversion, decoder packing, batch depth maximum.
+#include "ens_common.cuh"
+
+namespace ens {
+
+// [32][V] <-> [V][32] through a padded 32x32 shared tile; both sides fully coalesced.
+// HBM-bound: 2 x 4 bytes per element.  Grid = ceil(V/32) CTAs of 32x8 threads.
+__global__ void __launch_bounds__(256) grid_to_native_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                             int64_t V) {
+  __shared__ float tile[32][33];
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int c = ty; c < 32; c += 8) {
+    int64_t v = v0 + tx;
+    tile[c][tx] = (v < V) ? src[(int64_t)c * V + v] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    int64_t v = v0 + r;
+    if (v < V) dst[v * 32 + tx] = tile[tx][r];
+  }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) grid_from_native_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                               int64_t V) {
+  __shared__ float tile[32][33];
+  const int64_t v0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    int64_t v = v0 + r;
+    tile[r][tx] = (v < V) ? src[v * 32 + tx] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = ty; c < 32; c += 8) {
+    int64_t v = v0 + tx;
+    if (v < V) {
+      float x = tile[tx][c];
+      if (ACC) dst[(int64_t)c * V + v] += x; else dst[(int64_t)c * V + v] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder packing: one thread per packed float, pulling from the per-tensor pointers
+// ---------------------------------------------------------------------------------------------
+struct PtrTable { const float *p[24]; };
+
+template <int CD, int NO>
+__global__ void pack_mlp_kernel(PtrTable t, float *__restrict__ out) {
+  using P = MlpPack<CD>;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P::total()) return;
+  float v = 0.f;
+  // state_dict order: fc_c.i.weight (2i), fc_c.i.bias (2i+1), _B (10), pts.i.weight (11+2i), pts.i.bias (12+2i),
+  // out.weight (21), out.bias (22)
+  if (idx < 3 * EMBP) {
+    int r = idx / EMBP, k = idx % EMBP;
+    v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f;
+  } else if (idx >= P::off_Wo()) {
+    int o = idx - P::off_Wo();
+    if (o < 128) {
+      int j = o / 4, n = o % 4;
+      v = (n < NO) ? t.p[21][n * 32 + j] : 0.f;
+    } else {
+      int n = o - 128;
+      v = (n < NO) ? t.p[22][n] : 0.f;
+    }
+  } else {
+    int i = 0;
+#pragma unroll
+    for (int l = 1; l < 5; ++l) if (idx >= P::off_layer(l)) i = l;
+    int o = idx - P::off_layer(i);
+    const int K = P::K(i);
+    if (o < K * 32) {                       // W_iT[k][j] = W_i[j][k]
+      int k = o / 32, j = o % 32;
+      v = t.p[11 + 2 * i][j * K + k];
+    } else if (o < K * 32 + 32) {
+      v = t.p[12 + 2 * i][o - K * 32];
+    } else if (o < K * 32 + 32 + CD * 32) {  // Wc_iT[k][j] = Wc_i[j][k]
+      int q = o - K * 32 - 32;
+      int k = q / 32, j = q % 32;
+      v = t.p[2 * i][j * CD + k];
+    } else {
+      v = t.p[2 * i + 1][o - K * 32 - 32 - CD * 32];
+    }
+  }
+  out[idx] = v;
+}
+
+__global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {
+  using P = CoarsePack;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P::total()) return;
+  float v = 0.f;
+  // state_dict order: pts.i.weight (2i), pts.i.bias (2i+1), out.weight (10), out.bias (11)
+  if (idx >= P::off_Wo()) {
+    int o = idx - P::off_Wo();
+    if (o < 128) {
+      int j = o / 4, n = o % 4;
+      v = (n == 0) ? t.p[10][j] : 0.f;
+    } else {
+      v = (o == 128) ? t.p[11][0] : 0.f;
+    }
+  } else {
+    int i = 0;
+#pragma unroll
+    for (int l = 1; l < 5; ++l) if (idx >= P::off_W(l)) i = l;
+    int o = idx - P::off_W(i);
+    const int K = P::K(i);
+    if (o < K * 32) {
+      int k = o / 32, j = o % 32;
+      v = t.p[2 * i][j * K + k];
+    } else {
+      v = t.p[2 * i + 1][o - K * 32];
+    }
+  }
+  out[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// max(gt_depth): one CTA, grid-stride.  NaN-propagating like torch.max.  n is at most a few 100k.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) depth_max_kernel(const float *__restrict__ d, int64_t n,
+                                                         double *__restrict__ out) {
+  __shared__ float red[32];
+  __shared__ int nan_seen;
+  if (threadIdx.x == 0) nan_seen = 0;
+  __syncthreads();
+  float m = -INFINITY;
+  bool nan = false;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = d[i];
+    nan |= (v != v);
+    m = fmaxf(m, v);
+  }
+  if (nan) nan_seen = 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      if (nan_seen) m = NAN;
+      out[0] = (double)__fmul_rn(m, 1.2f);   // max(gt_depth*1.2): float32 product, monotone in gt_depth
+      out[1] = (double)m;
+    }
+  }
+}
+
+}  // namespace ens
+
+using namespace ens;
+
+extern "C" int ens_grid_to_native(const float *ref_layout, float *native, int64_t n_vox, ens_stream_t stream) {
+  if (!ref_layout || !native || n_vox < 0) return ENS_EINVAL;
+  if (n_vox == 0) return ENS_OK;
+  dim3 blk(32, 8);
+  grid_to_native_kernel<<<(unsigned)((n_vox + 31) / 32), blk, 0, (cudaStream_t)stream>>>(ref_layout, native, n_vox);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+extern "C" int ens_grid_from_native(const float *native, float *ref_layout, int64_t n_vox, int accumulate,
+                                    ens_stream_t stream) {
+  if (!ref_layout || !native || n_vox < 0) return ENS_EINVAL;
+  if (n_vox == 0) return ENS_OK;
+  dim3 blk(32, 8);
+  unsigned g = (unsigned)((n_vox + 31) / 32);
+  if (accumulate)
+    grid_from_native_kernel<true><<<g, blk, 0, (cudaStream_t)stream>>>(native, ref_layout, n_vox);
+  else
+    grid_from_native_kernel<false><<<g, blk, 0, (cudaStream_t)stream>>>(native, ref_layout, n_vox);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+extern "C" int ens_pack_decoder(int level, const float *const *tensors_host, int n_tensors, float *packed,
+                                ens_stream_t stream) {
+  if (!tensors_host || !packed) return ENS_EINVAL;
+  if (level < 0 || level > 3) return ENS_EINVAL;
+  const int need = (level == ENS_LEVEL_COARSE) ? 12 : 23;
+  if (n_tensors != need) return ENS_ESHAPE;
+  PtrTable t;
+  for (int i = 0; i < 24; ++i) t.p[i] = (i < n_tensors) ? tensors_host[i] : nullptr;
+  for (int i = 0; i < n_tensors; ++i) if (!t.p[i]) return ENS_EINVAL;
+  const int total = packed_floats(level);
+  const int nb = (total + 255) / 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (level) {
+    case ENS_LEVEL_COARSE: pack_coarse_kernel<<<nb, 256, 0, s>>>(t, packed); break;
+    case ENS_LEVEL_MIDDLE: pack_mlp_kernel<32, 1><<<nb, 256, 0, s>>>(t, packed); break;
+    case ENS_LEVEL_FINE: pack_mlp_kernel<64, 1><<<nb, 256, 0, s>>>(t, packed); break;
+    default: pack_mlp_kernel<32, 4><<<nb, 256, 0, s>>>(t, packed); break;
+  }
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+extern "C" int ens_depth_max(const float *gt_depth, int64_t n, double *out, ens_stream_t stream) {
+  if (!gt_depth || !out || n <= 0) return ENS_EINVAL;
+  depth_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt_depth, n, out);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}

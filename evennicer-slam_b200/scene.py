@@ -1,0 +1,140 @@
+"""Device-side scene state for the fused renderer: native-layout grids and packed decoders.
+
+The reference keeps the scene as ``c`` (dict ``'grid_<level>' -> float32 [1,32,Z,Y,X]``,
+EvenNICER_SLAM.py:217-275) and ``decoders`` (an ``nn.Module`` with one ``nn.Parameter`` per
+tensor, decoder.py:277-310).  Both are mutated in place between calls (Mapper.py:451-458,
+633-641; Adam), and shared across processes.  The kernels want one 128-byte line per voxel
+and one contiguous blob per decoder, so every call converts what changed:
+
+  * a grid is re-laid-out only if the tensor OBJECT or its ``_version`` differs from the
+    cached one (tracking: same clone for all 10 iterations -> converted once per frame;
+    mapping: mutated every iteration -> converted every iteration);
+  * a decoder is re-packed only if one of its parameters changed version.
+
+Caches hold weak references, so a recycled ``data_ptr`` can never alias a dead tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LEVELS, STAGE_LEVELS, EnsScene
+
+
+def decoder_tensors(decoders, level: str):
+    """Parameters of one decoder in state_dict order (the order ens_pack_decoder expects)."""
+    dec = getattr(decoders, level + "_decoder")
+    return [p for _, p in dec.named_parameters()]
+
+
+def decoder_grad_views(flat: torch.Tensor, params: Sequence[torch.Tensor]):
+    """Views of the flat per-decoder gradient buffer, one per parameter (reference shapes)."""
+    out, off = [], 0
+    for p in params:
+        n = p.numel()
+        out.append(flat[off:off + n].view(p.shape))
+        off += n
+    assert off == flat.numel(), (off, flat.numel())
+    return out
+
+
+class _GridEntry:
+    __slots__ = ("ref", "version", "native")
+
+
+class _DecEntry:
+    __slots__ = ("refs", "versions", "packed")
+
+
+class SceneCache:
+    """Per-Renderer cache of native grids / packed decoders, with version checks."""
+
+    def __init__(self):
+        self._grids: Dict[Tuple[str, int], _GridEntry] = {}
+        self._decs: Dict[Tuple[str, int], _DecEntry] = {}
+        self.stats = {"grid_convert": 0, "grid_hit": 0, "dec_pack": 0, "dec_hit": 0}
+
+    # -- grids ---------------------------------------------------------------------------
+    def native_grid(self, level: str, grid: torch.Tensor) -> torch.Tensor:
+        if grid.dim() != 5 or grid.shape[0] != 1 or grid.shape[1] != 32:
+            raise ValueError(f"grid_{level} must be [1,32,Z,Y,X], got {tuple(grid.shape)}")
+        if grid.dtype != torch.float32 or not grid.is_cuda:
+            raise ValueError(f"grid_{level} must be a float32 CUDA tensor")
+        key = (level, grid.device.index)
+        e = self._grids.get(key)
+        if e is not None and e.ref() is grid and e.version == grid._version:
+            self.stats["grid_hit"] += 1
+            return e.native
+        src = grid.detach()
+        if not src.is_contiguous():
+            src = src.contiguous()
+        Z, Y, X = grid.shape[2:]
+        # always a fresh buffer: an earlier forward may still hold the old one for its backward
+        native = torch.empty((Z, Y, X, 32), dtype=torch.float32, device=grid.device)
+        L = _lib.lib()
+        _lib.check(L.ens_grid_to_native(_lib.ptr(src), _lib.ptr(native), Z * Y * X,
+                                        _lib.cur_stream(grid.device)), "ens_grid_to_native")
+        e = _GridEntry()
+        e.ref, e.version, e.native = weakref.ref(grid), grid._version, native
+        self._grids[key] = e
+        self.stats["grid_convert"] += 1
+        return native
+
+    # -- decoders ------------------------------------------------------------------------
+    def packed_decoder(self, level: str, params: Sequence[torch.Tensor]) -> torch.Tensor:
+        dev = params[0].device
+        key = (level, dev.index)
+        e = self._decs.get(key)
+        if e is not None and len(e.refs) == len(params) and all(
+                r() is p and v == p._version for r, v, p in zip(e.refs, e.versions, params)):
+            self.stats["dec_hit"] += 1
+            return e.packed
+        L = _lib.lib()
+        li = LEVELS.index(level)
+        n = L.ens_decoder_num_tensors(li)
+        if len(params) != n:
+            raise ValueError(f"{level} decoder: expected {n} tensors, got {len(params)}")
+        keep = []
+        arr = (C.c_void_p * n)()
+        for i, p in enumerate(params):
+            if p.dtype != torch.float32 or not p.is_cuda:
+                raise ValueError("decoder parameters must be float32 CUDA tensors")
+            t = p.detach()
+            if not t.is_contiguous():
+                t = t.contiguous()
+            keep.append(t)
+            arr[i] = t.data_ptr()
+        packed = torch.empty(int(L.ens_packed_decoder_floats(li)), dtype=torch.float32, device=dev)
+        _lib.check(L.ens_pack_decoder(li, arr, n, _lib.ptr(packed), _lib.cur_stream(dev)), "ens_pack_decoder")
+        e = _DecEntry()
+        e.refs = [weakref.ref(p) for p in params]
+        e.versions = [p._version for p in params]
+        e.packed = packed
+        self._decs[key] = e
+        self.stats["dec_pack"] += 1
+        return packed
+
+
+def build_scene_struct(bound: torch.Tensor, coarse_bound: torch.Tensor,
+                       native_grids: Dict[str, torch.Tensor], packed: Dict[str, torch.Tensor]) -> EnsScene:
+    """Fill the C struct.  ``bound`` values are read on the host (they are CPU float64 in the
+    reference: EvenNICER_SLAM.py:170-175)."""
+    sc = EnsScene()
+    b = bound.detach().to("cpu", torch.float64)
+    cb = coarse_bound.detach().to("cpu", torch.float64)
+    for k in range(3):
+        sc.bound[k][0], sc.bound[k][1] = float(b[k, 0]), float(b[k, 1])
+        sc.coarse_bound[k][0], sc.coarse_bound[k][1] = float(cb[k, 0]), float(cb[k, 1])
+    for li, lv in enumerate(LEVELS):
+        g = native_grids.get(lv)
+        if g is not None:
+            sc.grid[li] = g.data_ptr()
+            sc.dims[li][0], sc.dims[li][1], sc.dims[li][2] = g.shape[0], g.shape[1], g.shape[2]
+        w = packed.get(lv)
+        if w is not None:
+            sc.weights[li] = w.data_ptr()
+    return sc

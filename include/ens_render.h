@@ -1,0 +1,167 @@
+/*
+ * ens_render.h -- C ABI of the B200-native fused ray renderer for EvenNICER-SLAM.
+ *
+ * The reference has no FFI layer: its seam is the Python call signatures of
+ * Renderer / NICE / get_samples.  Each entry point below names the
+ * reference function whose body it replaces (paths relative to /root/reference).
+ * The Python drop-ins in evennicer-slam_b200/ bind these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, gradient accumulators, workspace);
+ *     the library never allocates, frees or retains a pointer after return;
+ *   - all work is enqueued on `stream` (a cudaStream_t) and returns without host sync;
+ *   - return value 0 = ENS_OK, negative = error (ens_strerror);  no aborts, no exceptions;
+ *   - gradient buffers are ACCUMULATED INTO (caller zero-initialises);
+ *   - no global mutable state: safe from several processes / threads on one GPU.
+ *
+ * Layouts
+ *   - "reference" grid layout: float32 [32][Z][Y][X]  (torch [1,32,Z,Y,X], EvenNICER_SLAM.py:241-273)
+ *   - "native"    grid layout: float32 [Z][Y][X][32]  (one 128-byte line per voxel) -- what the
+ *     render kernels read and scatter into; ens_grid_to_native / ens_grid_from_native convert.
+ *   - decoder weights: a packed blob per decoder built by ens_pack_decoder from the decoder's
+ *     individual tensors in state_dict order; decoder gradients come back as ONE flat float32
+ *     buffer per decoder holding the tensors back-to-back in state_dict order and reference
+ *     shapes (so the host can hand out views).
+ */
+#ifndef ENS_RENDER_H_
+#define ENS_RENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENS_ABI_VERSION 1
+
+typedef void *ens_stream_t; /* cudaStream_t */
+
+enum {
+  ENS_OK = 0,
+  ENS_EINVAL = -1,       /* null pointer / bad enum / negative size */
+  ENS_ESHAPE = -2,       /* inconsistent sizes */
+  ENS_ECUDA = -3,        /* a CUDA call failed; cudaGetLastError is preserved */
+  ENS_ENCCL = -4,        /* reserved (collectives live in torch.distributed) */
+  ENS_EUNSUPPORTED = -5  /* iMAP modes: N_importance>0, occupancy=False, perturb>0, lindisp */
+};
+
+/* stage of NICE.forward (src/conv_onet/models/decoder.py:312-342) */
+enum { ENS_STAGE_COARSE = 0, ENS_STAGE_MIDDLE = 1, ENS_STAGE_FINE = 2, ENS_STAGE_COLOR = 3 };
+/* grid level / decoder index */
+enum { ENS_LEVEL_COARSE = 0, ENS_LEVEL_MIDDLE = 1, ENS_LEVEL_FINE = 2, ENS_LEVEL_COLOR = 3 };
+
+#define ENS_C_DIM 32          /* configs/nice_slam.yaml:111 (model.c_dim)  */
+#define ENS_HIDDEN 32         /* decoder.py:295 (hidden_size)              */
+#define ENS_EMBED 93          /* decoder.py:127 (Fourier mapping size)     */
+#define ENS_MAX_SAMPLES 64    /* N_samples + N_surface upper bound per ray */
+
+/* Scene = what `c` (dict of grids) + `decoders` carry in the reference. */
+typedef struct EnsScene {
+  const float *grid[4];        /* native layout, indexed by ENS_LEVEL_*; NULL if absent       */
+  int32_t dims[4][3];          /* (Z,Y,X) per level                                            */
+  double bound[3][2];          /* slam.bound: used by middle/fine/color decoders and the mask  */
+  double coarse_bound[3][2];   /* bound * coarse_bound_enlarge (EvenNICER_SLAM.py:182)         */
+  const float *weights[4];     /* packed decoder blobs from ens_pack_decoder; NULL if absent   */
+} EnsScene;
+
+/* rendering knobs (cfg['rendering'], Renderer.py:11-19) */
+typedef struct EnsRenderCfg {
+  int32_t n_samples;           /* N_samples   (32)                                             */
+  int32_t n_surface;           /* N_surface   (16); forced to 0 without gt_depth / stage coarse */
+  int32_t n_importance;        /* must be 0                                                     */
+  int32_t lindisp;             /* must be 0                                                     */
+  float perturb;               /* must be 0                                                     */
+  int32_t occupancy;           /* must be 1                                                     */
+  const float *t_vals;         /* device float32 [n_samples]: torch.linspace(0,1,N_samples)      */
+  const double *t_vals_surface;/* device float64 [n_surface]: torch.linspace(0,1,N_surface).double() */
+} EnsRenderCfg;
+
+/* gradient sinks of ens_render_bwd; any member may be NULL (= not needed). */
+typedef struct EnsGrads {
+  float *grid[4];              /* native layout, accumulate-into                                */
+  float *decoder[4];           /* flat per-decoder buffers (state_dict order), accumulate-into   */
+  float *rays_o;               /* [R][3], written (not accumulated)                              */
+  float *rays_d;               /* [R][3], written                                                */
+} EnsGrads;
+
+int ens_version(void);
+const char *ens_strerror(int code);
+
+/* number of floats in a packed decoder blob / in the flat gradient buffer of a decoder */
+int64_t ens_packed_decoder_floats(int level);
+int64_t ens_decoder_grad_floats(int level);
+/* number of tensors in a decoder's state_dict (22 for coarse-less MLPs: 10 fc_c + _B + 10 pts + 2 out = 23; 12 coarse) */
+int ens_decoder_num_tensors(int level);
+/* bytes of scratch ens_render_bwd needs for R rays x S samples when decoder grads are requested */
+int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads);
+
+/* [32][Z][Y][X] -> [Z][Y][X][32]  and back.  n_vox = Z*Y*X.  (layout of `c`, EvenNICER_SLAM.py:217-275) */
+int ens_grid_to_native(const float *ref_layout, float *native, int64_t n_vox, ens_stream_t stream);
+int ens_grid_from_native(const float *native, float *ref_layout, int64_t n_vox, int accumulate,
+                         ens_stream_t stream);
+
+/* Gather a decoder's individual tensors (device pointers, state_dict order, listed in a HOST array)
+ * into the packed blob the kernels stage into shared memory.  Replaces nothing in the reference; it
+ * is the price of accepting nn.Parameter-per-tensor storage (decoder.py:108-164, 224-250). */
+int ens_pack_decoder(int level, const float *const *tensors_host, int n_tensors, float *packed,
+                     ens_stream_t stream);
+
+/* max(gt_depth) -> out[0] = (double)(max*1.2f)  [Renderer.py:110],  out[1] = (double)max  [Renderer.py:145].
+ * `out` is a device double[2]; pass it to ens_render_fwd/bwd as depth_max. */
+int ens_depth_max(const float *gt_depth, int64_t n, double *out, ens_stream_t stream);
+
+/* common.get_samples (src/common.py:92-187) after the torch.randint draw: for each flat index into
+ * the crop [H0:H1, W0:W1] produce pixel coords, gathered depth (f32) / colour (f64 or f32) and the ray
+ * (get_rays_from_uv, common.py:74-89) for c2w (device float32, row stride `c2w_stride` >= 4, 3 rows). */
+int ens_sample_rays(const int64_t *indices, int64_t n, int H0, int H1, int W0, int W1, int H, int W,
+                    float fx, float fy, float cx, float cy, const float *c2w, int c2w_stride,
+                    const float *depth, const void *color, int color_is_f64,
+                    float *pix_i, float *pix_j, float *rays_o, float *rays_d, float *out_depth,
+                    void *out_color, ens_stream_t stream);
+
+/* common.get_rays / get_rays_rescale (src/common.py:300-340): rays of an (nH x nW) pixel lattice whose
+ * coordinates are lin_w[nW], lin_h[nH] (device float32: the reference's torch.linspace vectors).
+ * nH == 0 selects "pairs" mode: nW rays with pixel (lin_w[k], lin_h[k]) = get_rays_from_uv (common.py:74-89). */
+int ens_lattice_rays(const float *lin_w, int nW, const float *lin_h, int nH, float fx, float fy, float cx,
+                     float cy, const float *c2w, int c2w_stride, float *rays_o, float *rays_d,
+                     ens_stream_t stream);
+
+/* backward of both ray generators into c2w: g_c2w (device float32 [3][4], accumulate-into).
+ * pix_i/pix_j are the per-ray pixel coordinates (for a lattice: pass lin_w/lin_h with nW>0). */
+int ens_rays_bwd(const float *pix_i, const float *pix_j, int64_t n, int nW, float fx, float fy, float cx,
+                 float cy, const float *g_rays_o, const float *g_rays_d, float *g_c2w,
+                 ens_stream_t stream);
+
+/* Renderer.eval_points (src/utils/Renderer.py:24-62; clone at src/utils/Mesher.py:281-319):
+ * pts [N][3] float64 or float32 -> out [N][4] float32 (r,g,b,occ).  apply_bound_mask != 0 applies the
+ * `ret[~mask,3] = 100` rule for points outside slam.bound (Renderer.py:43-58); 0 gives the bare
+ * NICE.forward (src/conv_onet/models/decoder.py:312-342) that Mesher.eval_points calls. */
+int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_is_f64, int64_t n,
+                    int apply_bound_mask, float *out4, ens_stream_t stream);
+
+/* Renderer.render_batch_ray forward (src/utils/Renderer.py:64-199) with raw2outputs_nerf_color
+ * (src/common.py:256-297).  gt_depth may be NULL (and is ignored for stage coarse); depth_max is the
+ * device double[2] from ens_depth_max (NULL iff gt_depth is NULL).
+ * Outputs: depth f64 [R], var f64 [R], color f32 [R][3].  Optional (may be NULL): z_vals f64 [R][S],
+ * weights f32 [R][S], raw f32 [R][S][4] (pre-sigmoid; `raw` is also what ens_render_bwd wants back). */
+int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
+                   const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
+                   double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,
+                   ens_stream_t stream);
+
+/* Backward of ens_render_fwd into grid features, decoder weights and rays.
+ * Recomputes sample placement and activations; `raw` is the [R][S][4] tensor saved by the forward.
+ * g_depth f64 [R], g_var f64 [R], g_color f32 [R][3]; any may be NULL (= zero).
+ * workspace: ens_bwd_workspace_bytes bytes (only touched when decoder grads are requested). */
+int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
+                   const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
+                   const float *raw, const double *g_depth, const double *g_var, const float *g_color,
+                   const EnsGrads *grads, void *workspace, int64_t workspace_bytes, ens_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENS_RENDER_H_ */

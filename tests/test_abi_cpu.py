@@ -1,0 +1,76 @@
+"""CPU checks of the boundary: the library builds/loads and exports every symbol the header declares;
+host-side helpers behave.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    from evennicer_slam_b200 import _lib
+    return _lib
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "ens_render.h")).read()
+    declared = set(re.findall(r"\b(ens_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    handle = ctypes.CDLL(built.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in ens_render.h but not exported"
+    assert declared == set(built.EXPORTED_SYMBOLS), declared ^ set(built.EXPORTED_SYMBOLS)
+
+
+def test_sizes_match_reference_parameter_counts(built):
+    L = built.lib()
+    # middle 15 800, fine 20 920, colour 15 899, coarse 6 337 parameters
+    assert [L.ens_decoder_grad_floats(i) for i in range(4)] == [6337, 15800, 20920, 15899]
+    assert [L.ens_decoder_num_tensors(i) for i in range(4)] == [12, 23, 23, 23]
+    assert L.ens_packed_decoder_floats(1) % 4 == 0 and L.ens_packed_decoder_floats(2) % 4 == 0
+    assert L.ens_bwd_workspace_bytes(1000, 48, 0) == 0
+    assert L.ens_bwd_workspace_bytes(1000, 48, 1) == (48000 + 1) * 160 * 4
+    import evennicer_slam_b200.synthetic as syn
+    for li, lv in enumerate(syn.LEVELS):
+        n = sum(int(np.prod(s)) for _, s in syn.decoder_param_shapes(lv))
+        assert n == L.ens_decoder_grad_floats(li)
+
+
+def test_error_codes_without_gpu(built):
+    L = built.lib()
+    assert L.ens_strerror(0) == b"ok"
+    assert L.ens_grid_to_native(None, None, 1, None) == -1          # ENS_EINVAL before any CUDA call
+    assert L.ens_eval_points(None, 0, None, 1, 0, 1, None, None) == -1
+    assert L.ens_pack_decoder(7, None, 0, None, None) == -1
+
+
+def test_dropin_state_dict_keys_match_reference_layout():
+    import torch
+    from evennicer_slam_b200.decoder import NICE
+    import evennicer_slam_b200.synthetic as syn
+    m = NICE(coarse=True)
+    for lv in syn.LEVELS:
+        dec = getattr(m, lv + "_decoder")
+        got = [(k, tuple(v.shape)) for k, v in dec.state_dict().items()]
+        assert got == syn.decoder_param_shapes(lv), lv
+    import copy
+    m2 = copy.deepcopy(m)
+    assert m2._ens_cache is None and len(list(m2.parameters())) == len(list(m.parameters()))
+
+
+def test_render_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import cases
+    from evennicer_slam_b200 import harness
+    scene = cases.tiny_scene()
+    decoders, c, renderer, cfg = harness.build(scene, "cpu")
+    with pytest.raises((RuntimeError, ValueError)):
+        renderer.render_batch_ray(c, decoders, torch.zeros(4, 3), torch.zeros(4, 3), "cpu", "color")

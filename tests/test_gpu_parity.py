@@ -1,0 +1,324 @@
+"""Parity of the CUDA path (through the C ABI / the Python drop-ins) with the oracle and the
+reference-generated goldens.  Needs a B200 (``-m gpu``).
+
+Tolerances (BASELINE.json north_star): pixel indices and sample placement bit-exact; rendered
+depth / colour 1e-4 relative; gradients 1e-3 relative (atomic ordering).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import render_oracle as orc
+from util import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+STAGES = ("coarse", "middle", "fine", "color")
+DEV = "cuda:0"
+TOL_OUT = 1e-4
+TOL_GRAD = 1e-3
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from evennicer_slam_b200 import harness
+    scene = cases.tiny_scene()
+    decoders, c, renderer, cfg = harness.build(scene, DEV)
+    cam_t, depth, color, event = cases.tiny_frame()
+    return dict(scene=scene, decoders=decoders, c=c, renderer=renderer, cam_t=cam_t, depth=depth,
+                color=color, g=load_golden("tiny_render.npz"), sc=orc.OracleScene.from_synthetic(scene))
+
+
+def test_library_loads_and_reports_version():
+    from evennicer_slam_b200 import _lib
+    L = _lib.lib()
+    assert L.ens_version() == 1
+    assert L.ens_packed_decoder_floats(2) == 21028 and L.ens_decoder_grad_floats(3) == 15899
+
+
+def test_grid_layout_roundtrip():
+    from evennicer_slam_b200 import _lib
+    L = _lib.lib()
+    g = torch.randn(1, 32, 5, 7, 9, device=DEV)
+    nat = torch.empty(5, 7, 9, 32, device=DEV)
+    _lib.check(L.ens_grid_to_native(_lib.ptr(g), _lib.ptr(nat), 5 * 7 * 9, _lib.cur_stream(g.device)))
+    assert torch.equal(nat, g[0].permute(1, 2, 3, 0).contiguous())
+    back = torch.zeros_like(g)
+    _lib.check(L.ens_grid_from_native(_lib.ptr(nat), _lib.ptr(back), 5 * 7 * 9, 0, _lib.cur_stream(g.device)))
+    assert torch.equal(back, g)
+    _lib.check(L.ens_grid_from_native(_lib.ptr(nat), _lib.ptr(back), 5 * 7 * 9, 1, _lib.cur_stream(g.device)))
+    assert torch.equal(back, 2 * g)
+
+
+def test_get_samples_bit_exact(tiny):
+    """Pixel draw + gather + ray generation vs. the golden AND vs. the reference's own expression on the GPU."""
+    from evennicer_slam_b200 import common
+    scene, g = tiny["scene"], tiny["g"]
+    cam = scene.cam
+    c2w = torch.from_numpy(g["color.d.c2w"]).to(DEV)
+    depth = torch.from_numpy(tiny["depth"]).to(DEV)
+    color = torch.from_numpy(tiny["color"]).to(DEV)
+    torch.manual_seed(cases.SEED)
+    gen_idx = torch.randint(cam.H * cam.W, (cases.N_TINY_RAYS,), device=DEV)
+    torch.manual_seed(cases.SEED)
+    ro, rd, sd, scol = common.get_samples(0, cam.H, 0, cam.W, cases.N_TINY_RAYS, cam.H, cam.W, cam.fx, cam.fy,
+                                          cam.cx, cam.cy, c2w, depth, color, DEV)
+    # same generator state -> same indices as an explicit randint on this device
+    i, j, d_ref, c_ref = orc.select_pixels(gen_idx.cpu().numpy(), 0, cam.H, 0, cam.W, tiny["depth"], tiny["color"])
+    assert np.array_equal(sd.cpu().numpy(), d_ref) and np.array_equal(scol.cpu().numpy(), c_ref)
+    ro_ref, rd_ref = orc.rays_from_uv(i, j, g["color.d.c2w"], cam.fx, cam.fy, cam.cx, cam.cy)
+    assert np.array_equal(rd.cpu().numpy(), rd_ref) and np.array_equal(ro.cpu().numpy(), ro_ref)
+    # the reference's eager expression evaluated by torch on this GPU (common.py:80-88)
+    ti, tj = torch.from_numpy(i).to(DEV), torch.from_numpy(j).to(DEV)
+    dirs = torch.stack([(ti - cam.cx) / cam.fx, -(tj - cam.cy) / cam.fy, -torch.ones_like(ti)], -1).reshape(-1, 1, 3)
+    rd_eager = torch.sum(dirs * c2w[:3, :3], -1)
+    assert torch.equal(rd, rd_eager)
+
+
+def test_get_samples_indices_match_cpu_golden_when_generators_agree(tiny):
+    """torch's CPU and CUDA generators differ, so golden indices (CPU) are checked by feeding them
+    through the kernel rather than by re-drawing."""
+    from evennicer_slam_b200 import _lib
+    scene, g = tiny["scene"], tiny["g"]
+    cam = scene.cam
+    L = _lib.lib()
+    idx = torch.from_numpy(g["indices"]).to(DEV)
+    n = idx.numel()
+    c2w = torch.from_numpy(g["color.d.c2w"]).to(DEV)
+    depth = torch.from_numpy(tiny["depth"]).to(DEV)
+    color = torch.from_numpy(tiny["color"]).to(DEV)
+    ro = torch.empty(n, 3, device=DEV); rd = torch.empty(n, 3, device=DEV)
+    sd = torch.empty(n, device=DEV); sc = torch.empty(n, 3, dtype=torch.float64, device=DEV)
+    _lib.check(L.ens_sample_rays(_lib.ptr(idx), n, 0, cam.H, 0, cam.W, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy,
+                                 _lib.ptr(c2w), c2w.stride(0), _lib.ptr(depth), _lib.ptr(color), 1, None, None,
+                                 _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(sd), _lib.ptr(sc), _lib.cur_stream(idx.device)))
+    assert np.array_equal(rd.cpu().numpy(), g["color.d.rays_d"])
+    assert np.array_equal(ro.cpu().numpy(), g["color.d.rays_o"])
+    assert np.array_equal(sd.cpu().numpy(), g["color.d.sample_depth"])
+    assert np.array_equal(sc.cpu().numpy(), g["color.d.sample_color"])
+
+
+@pytest.mark.parametrize("stage", STAGES)
+def test_eval_points(tiny, stage):
+    scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
+    g = load_golden("tiny_eval_points.npz")
+    pts = cases.eval_points_lattice(scene)
+    out = renderer.eval_points(torch.from_numpy(pts).to(DEV), decoders, c, stage, DEV).cpu().numpy()
+    ref = g[f"{stage}.f64"]
+    assert np.array_equal(out[:, 3] == 100, ref[:, 3] == 100)
+    assert rel_err(out, ref) < TOL_OUT
+    oracle, _ = orc.eval_points(tiny["sc"], pts, stage)
+    assert rel_err(out, oracle) < TOL_OUT
+    out32 = renderer.eval_points(torch.from_numpy(pts.astype(np.float32)).to(DEV), decoders, c, stage, DEV).cpu().numpy()
+    ref32 = g[f"{stage}.f32"]
+    assert np.array_equal(out32[:, 3] == 100, ref32[:, 3] == 100)
+    assert rel_err(out32, ref32) < TOL_OUT
+    # NICE.forward: same decode without the bound rule (Mesher.py:308)
+    bare = decoders(torch.from_numpy(pts).to(DEV)[None], c_grid=c, stage=stage).cpu().numpy()
+    inside = ref[:, 3] != 100
+    assert rel_err(bare[inside], ref[inside]) < TOL_OUT and not np.any(bare[:, 3] == 100)
+
+
+def _run_case(tiny, stage, use_depth, with_params=True):
+    renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
+    tag = f"{stage}.{'d' if use_depth else 'n'}"
+    for p in decoders.parameters():
+        p.grad = None
+        p.requires_grad_(with_params)
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    ro = torch.from_numpy(g[f"{tag}.rays_o"]).to(DEV).requires_grad_(True)
+    rd = torch.from_numpy(g[f"{tag}.rays_d"]).to(DEV).requires_grad_(True)
+    sd = torch.from_numpy(g[f"{tag}.sample_depth"]).to(DEV)
+    out = renderer.render_batch_ray_aux(cg, decoders, rd, ro, DEV, stage, gt_depth=sd if use_depth else None)
+    return tag, cg, ro, rd, out
+
+
+@pytest.mark.parametrize("stage", STAGES)
+@pytest.mark.parametrize("use_depth", [True, False])
+def test_render_forward(tiny, stage, use_depth):
+    g = tiny["g"]
+    tag, cg, ro, rd, (depth, var, color, raw, z, w) = _run_case(tiny, stage, use_depth)
+    assert depth.dtype == torch.float64 and var.dtype == torch.float64 and color.dtype == torch.float32
+    assert np.array_equal(z.cpu().numpy(), g[f"{tag}.z_vals"]), "sample placement must be bit-exact"
+    assert rel_err(raw.cpu().numpy(), g[f"{tag}.raw"]) < TOL_OUT
+    assert rel_err(depth.detach().cpu().numpy(), g[f"{tag}.depth"]) < TOL_OUT
+    assert rel_err(var.detach().cpu().numpy(), g[f"{tag}.var"]) < TOL_OUT
+    if stage == "color":
+        assert rel_err(color.detach().cpu().numpy(), g[f"{tag}.color"]) < TOL_OUT
+    else:
+        assert float(color.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("stage", STAGES)
+@pytest.mark.parametrize("use_depth", [True, False])
+def test_render_backward(tiny, stage, use_depth):
+    g, decoders = tiny["g"], tiny["decoders"]
+    tag, cg, ro, rd, (depth, var, color, raw, z, w) = _run_case(tiny, stage, use_depth)
+    g_d, g_v, g_c = cases.upstream_grads(ro.shape[0])
+    loss = (depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum() \
+        + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()
+    loss.backward()
+    assert rel_err(ro.grad.cpu().numpy(), g[f"{tag}.g_rays_o"]) < TOL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), g[f"{tag}.g_rays_d"]) < TOL_GRAD
+    for name in orc.STAGE_DECODERS[stage]:
+        gk = "grid_" + name
+        assert rel_err(cg[gk].grad.cpu().numpy(), g[f"{tag}.ggrid.{gk}"]) < TOL_GRAD, gk
+        for key, p in getattr(decoders, name + "_decoder").named_parameters():
+            ref = g[f"{tag}.gdec.{name}.{key}"]
+            got = p.grad.cpu().numpy()
+            if np.abs(ref).max() == 0:
+                assert np.abs(got).max() == 0, (name, key)
+            else:
+                assert rel_err(got, ref) < TOL_GRAD, (name, key)
+    for lv in STAGES:   # untouched levels get no gradient
+        if lv not in orc.STAGE_DECODERS[stage]:
+            assert cg["grid_" + lv].grad is None
+
+
+def test_backward_without_decoder_or_grid_grads_matches(tiny):
+    """Tracker-style call: only the rays need gradient (decoder/grid grads skipped in the kernel)."""
+    g = tiny["g"]
+    renderer, decoders, c = tiny["renderer"], tiny["decoders"], tiny["c"]
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+    tag = "color.d"
+    ro = torch.from_numpy(g[f"{tag}.rays_o"]).to(DEV).requires_grad_(True)
+    rd = torch.from_numpy(g[f"{tag}.rays_d"]).to(DEV).requires_grad_(True)
+    sd = torch.from_numpy(g[f"{tag}.sample_depth"]).to(DEV)
+    depth, var, color = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=sd)
+    g_d, g_v, g_c = cases.upstream_grads(ro.shape[0])
+    ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+     + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    assert rel_err(ro.grad.cpu().numpy(), g[f"{tag}.g_rays_o"]) < TOL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), g[f"{tag}.g_rays_d"]) < TOL_GRAD
+    for p in decoders.parameters():
+        p.requires_grad_(True)
+
+
+def test_pose_gradient_end_to_end(tiny):
+    """camera_tensor -> get_camera_from_tensor -> get_samples -> render -> loss -> backward (Tracker.py:142-197)."""
+    from evennicer_slam_b200 import common, _lib
+    from evennicer_slam_b200.functional import _PairRays
+    scene, g = tiny["scene"], tiny["g"]
+    renderer, decoders, c = tiny["renderer"], tiny["decoders"], tiny["c"]
+    cam = scene.cam
+    ct = torch.from_numpy(tiny["cam_t"].copy()).to(DEV).requires_grad_(True)
+    c2w = common.get_camera_from_tensor(ct)
+    assert np.allclose(c2w.detach().cpu().numpy(), g["color.d.c2w"], atol=1e-6)
+    idx = g["indices"]
+    i, j, sd, _ = orc.select_pixels(idx, 0, cam.H, 0, cam.W, tiny["depth"], tiny["color"])
+    ro, rd = _PairRays.apply(c2w, torch.from_numpy(i).to(DEV), torch.from_numpy(j).to(DEV),
+                             (cam.H, cam.W, float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy)))
+    depth, var, color = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=torch.from_numpy(sd).to(DEV))
+    g_d, g_v, g_c = cases.upstream_grads(ro.shape[0])
+    ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+     + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    assert rel_err(ct.grad.cpu().numpy(), g["color.d.g_cam"]) < TOL_GRAD
+
+
+def test_full_frame_and_rescaled_frame(tiny):
+    scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
+    from evennicer_slam_b200 import common
+    g = load_golden("tiny_frames.npz")
+    cam = scene.cam
+    ct = torch.from_numpy(tiny["cam_t"].copy()).to(DEV).requires_grad_(True)
+    c2w = common.get_camera_from_tensor(ct)
+    ro, rd = common.get_rays(cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w.detach(), DEV)
+    assert np.array_equal(rd.cpu().numpy(), g["full.rays_d"]) and np.array_equal(ro.cpu().numpy(), g["full.rays_o"])
+    nH, nW = int(cam.H * 0.5), int(cam.W * 0.5)
+    ro2, rd2 = common.get_rays_rescale(cam.H, cam.W, nH, nW, cam.fx, cam.fy, cam.cx, cam.cy, c2w, DEV)
+    assert np.array_equal(rd2.detach().cpu().numpy(), g["rescale.rays_d"])
+    import evennicer_slam_b200.synthetic as syn
+    gsum = torch.from_numpy(syn.det_uniform((nH, nW, 3), 555).astype(np.float32)).to(DEV)
+    ((rd2 * gsum).sum() + (ro2 * gsum * 0.5).sum()).backward()
+    assert rel_err(ct.grad.cpu().numpy(), g["rescale.g_cam"]) < 1e-5
+    depth_img = torch.from_numpy(tiny["depth"]).to(DEV)
+    renderer.ray_batch_size = 1000          # several batches -> per-batch depth maxima, as in the reference...
+    d, u, col = renderer.render_img(c, decoders, c2w.detach(), DEV, "color", gt_depth=depth_img)
+    renderer.ray_batch_size = 100000
+    # ...but the golden used one 100k batch (3072 rays), so compare with a single batch too
+    d1, u1, col1 = renderer.render_img(c, decoders, c2w.detach(), DEV, "color", gt_depth=depth_img)
+    assert d1.dtype == torch.float64 and d1.shape == (cam.H, cam.W) and col1.shape == (cam.H, cam.W, 3)
+    assert rel_err(d1.cpu().numpy(), g["render_img.depth"]) < TOL_OUT
+    assert rel_err(u1.cpu().numpy(), g["render_img.var"]) < TOL_OUT
+    assert rel_err(col1.cpu().numpy(), g["render_img.color"]) < TOL_OUT
+    assert d.shape == d1.shape
+    ct2 = torch.from_numpy(tiny["cam_t"].copy()).to(DEV).requires_grad_(True)
+    c2w2 = common.get_camera_from_tensor(ct2)
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+    d, u, col = renderer.render_img_rescale(c, decoders, c2w2, DEV, "color", gt_depth=depth_img, scale_factor=0.5)
+    assert rel_err(d.detach().cpu().numpy(), g["render_img_rescale.depth"]) < TOL_OUT
+    assert rel_err(col.detach().cpu().numpy(), g["render_img_rescale.color"]) < TOL_OUT
+    (col * gsum).sum().backward()
+    assert rel_err(ct2.grad.cpu().numpy(), g["render_img_rescale.g_cam"]) < TOL_GRAD
+    for p in decoders.parameters():
+        p.requires_grad_(True)
+
+
+def test_room0_mapping_batch_vs_golden_and_oracle():
+    """Config C1/C3 shape: 1000 rays x 48 samples, colour stage, room0 grids (46 MiB)."""
+    from evennicer_slam_b200 import harness
+    scene = cases.room0_scene()
+    decoders, c, renderer, cfg = harness.build(scene, DEV)
+    g = load_golden("room0_color_1000.npz")
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    ro = torch.from_numpy(g["rays_o"]).to(DEV).requires_grad_(True)
+    rd = torch.from_numpy(g["rays_d"]).to(DEV).requires_grad_(True)
+    sd = torch.from_numpy(g["sample_depth"]).to(DEV)
+    depth, var, color, raw, z, w = renderer.render_batch_ray_aux(cg, decoders, rd, ro, DEV, "color", gt_depth=sd)
+    assert np.array_equal(z.cpu().numpy(), g["z_vals"])
+    assert rel_err(depth.detach().cpu().numpy(), g["depth"]) < TOL_OUT
+    assert rel_err(var.detach().cpu().numpy(), g["var"]) < TOL_OUT
+    assert rel_err(color.detach().cpu().numpy(), g["color"]) < TOL_OUT
+    g_d, g_v, g_c = cases.upstream_grads(cases.N_ROOM0_RAYS)
+    ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+     + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    assert rel_err(ro.grad.cpu().numpy(), g["g_rays_o"]) < TOL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), g["g_rays_d"]) < TOL_GRAD
+    for name in ("fine", "color", "middle"):
+        for key, p in getattr(decoders, name + "_decoder").named_parameters():
+            ref = g[f"gdec.{name}.{key}"]
+            if np.abs(ref).max() > 0:
+                assert rel_err(p.grad.cpu().numpy(), ref) < TOL_GRAD, (name, key)
+        gk = "grid_" + name
+        flat = cg[gk].grad.reshape(-1).cpu().numpy()
+        assert rel_err(flat[g[f"ggrid.{gk}.probe_idx"]], g[f"ggrid.{gk}.probe_val"]) < TOL_GRAD
+        assert abs(np.abs(flat.astype(np.float64)).sum() - g[f"ggrid.{gk}.l1"]) < TOL_GRAD * g[f"ggrid.{gk}.l1"]
+        assert int((flat != 0).sum()) == int(g[f"ggrid.{gk}.nnz"])
+
+
+def test_scene_cache_tracks_in_place_updates(tiny):
+    """Mapper mutates grids in place every iteration (Mapper.py:451-458): results must follow."""
+    renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
+    tag = "middle.d"
+    ro = torch.from_numpy(g[f"{tag}.rays_o"]).to(DEV)
+    rd = torch.from_numpy(g[f"{tag}.rays_d"]).to(DEV)
+    sd = torch.from_numpy(g[f"{tag}.sample_depth"]).to(DEV)
+    c2 = {k: v.clone() for k, v in c.items()}
+    with torch.no_grad():
+        d0, _, _ = renderer.render_batch_ray(c2, decoders, rd, ro, DEV, "middle", gt_depth=sd)
+        hits = renderer._cache.stats["grid_hit"]
+        d1, _, _ = renderer.render_batch_ray(c2, decoders, rd, ro, DEV, "middle", gt_depth=sd)
+        assert renderer._cache.stats["grid_hit"] == hits + 1 and torch.equal(d0, d1)
+        c2["grid_middle"].mul_(0.5)
+        d2, _, _ = renderer.render_batch_ray(c2, decoders, rd, ro, DEV, "middle", gt_depth=sd)
+        assert not torch.equal(d0, d2)
+        c2["grid_middle"].mul_(2.0)
+        d3, _, _ = renderer.render_batch_ray(c2, decoders, rd, ro, DEV, "middle", gt_depth=sd)
+        assert torch.equal(d0, d3)
+
+
+def test_errors_are_reported_not_fatal(tiny):
+    from evennicer_slam_b200 import _lib
+    L = _lib.lib()
+    assert L.ens_grid_to_native(None, None, 10, None) == -1
+    assert b"unsupported" in L.ens_strerror(-5)
+    renderer, decoders, c = tiny["renderer"], tiny["decoders"], tiny["c"]
+    renderer.N_importance = 12
+    try:
+        with pytest.raises(RuntimeError, match="unsupported"):
+            renderer.render_batch_ray(c, decoders, torch.zeros(4, 3, device=DEV), torch.zeros(4, 3, device=DEV), DEV, "color")
+    finally:
+        renderer.N_importance = 0
