@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""Benchmark of the fused ray-rendering hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU baseline: the oracle port on host cores
+
+One JSON line on stdout.  A "step" is one pass of the hot path over one synthetic Replica mapping
+batch (config C3/C1 of SURVEY.md 8(d)): 5 frames x 200 px drawn with get_samples (4 BA poses carry
+gradient), colour-stage render_batch_ray over room0 grids (46 MiB), the Mapper loss
+(Mapper.py:553-562) and backward into grid features, all decoder weights and the camera tensors.
+The scene cache is invalidated every step (Mapper mutates the grids every iteration, Mapper.py:451-458),
+so the layout conversions are inside the timed region.  L2 is flushed between timed steps.
+
+  value  : rays/s, device-resident inputs, CUDA-event time summed over K steps (max over ranks)
+  e2e    : rays/s through the C-ABI-level call with HOST (pinned) ray buffers in, outputs + ray
+           gradients + loss out, copies inside the timed region
+  N > 1  : weak scaling -- every rank runs its own 1000-ray batch on a replicated scene and the grid /
+           decoder / pose gradients are SUM all-reduced over NCCL (inside the timed region)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_FRAMES = 5
+PIX_PER_FRAME = 200
+N_RAYS = N_FRAMES * PIX_PER_FRAME
+S_TOTAL = 48
+# algorithmic grid bytes: 1024 B per point per level; colour stage touches 3 levels
+BYTES_PER_POINT_FWD = 1024 * 3
+BYTES_PER_POINT_BWD = 1024 * 3 + 1024 * 3       # re-gather + scatter-add
+BYTES_PER_RAY = (BYTES_PER_POINT_FWD + BYTES_PER_POINT_BWD) * S_TOTAL   # 442 368
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs():
+    import cases
+    import evennicer_slam_b200.synthetic as syn
+    scene = cases.room0_scene()
+    frames = []
+    for f in range(N_FRAMES):
+        cam_t = syn.default_pose(syn.ROOM0_BOUND, jitter_seed=10 + f)
+        depth, color, _ = syn.synthetic_frame(syn.ROOM0_BOUND, syn.REPLICA_CAM, cam_t, seed=100 + f, zero_frac=0.02)
+        frames.append((cam_t, depth, color))
+    return scene, frames
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores
+# ---------------------------------------------------------------------------------------------
+def oracle_step(sc, frames, n_per_frame, seed, t32, t64):
+    """get_samples -> render_batch_ray -> Mapper loss -> backward with the numpy oracle; returns rays done."""
+    import evennicer_slam_b200.synthetic as syn
+    import render_oracle as orc
+    cam = syn.REPLICA_CAM
+    rng = np.random.RandomState(seed)
+    ros, rds, sds, scs = [], [], [], []
+    for (cam_t, depth, color) in frames:
+        idx = rng.randint(0, cam.H * cam.W, size=n_per_frame)
+        i, j, sd, scol = orc.select_pixels(idx, 0, cam.H, 0, cam.W, depth, color)
+        ro, rd = orc.rays_from_uv(i, j, syn.quat_to_c2w(cam_t), cam.fx, cam.fy, cam.cx, cam.cy)
+        ros.append(ro); rds.append(rd); sds.append(sd); scs.append(scol)
+    ro, rd, sd, scol = np.concatenate(ros), np.concatenate(rds), np.concatenate(sds), np.concatenate(scs)
+    dep, var, col, cache = orc.render_batch_ray(sc, ro, rd, "color", sd, t32, t64)
+    g_d = np.where(sd > 0, -np.sign(sd.astype(np.float64) - dep), 0.0)          # d/d depth of sum|gt-d|[gt>0]
+    g_c = (-0.2 * np.sign(scol.astype(np.float32) - col)).astype(np.float32)     # 0.2 * sum|gt-c|
+    grads = orc.render_batch_ray_backward(sc, cache, g_d, None, g_c)
+    for f in range(len(frames)):
+        sl = slice(f * n_per_frame, (f + 1) * n_per_frame)
+        orc.rays_from_uv_backward(np.zeros(n_per_frame), np.zeros(n_per_frame), cam.fx, cam.fy, cam.cx, cam.cy,
+                                  grads["rays_o"][sl], grads["rays_d"][sl])
+    return ro.shape[0]
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return int(max(n)) if n else 1
+    except Exception:
+        return 1
+
+
+def cpu_baseline(budget_s=20.0):
+    """Bounded sample of the mapping workload on the host cores (kind 'port': numpy oracle)."""
+    import torch
+    import render_oracle as orc
+    scene, frames = make_inputs()
+    sc = orc.OracleScene.from_synthetic(scene)
+    t32 = torch.linspace(0., 1., 32).numpy()
+    t64 = torch.linspace(0., 1., 16).double().numpy()
+    n_pf = 20                                            # 100-ray probe to size the sample
+    t0 = time.perf_counter()
+    n = oracle_step(sc, frames, n_pf, 0, t32, t64)
+    probe = time.perf_counter() - t0
+    rate = n / probe
+    n_pf = int(max(10, min(PIX_PER_FRAME, rate * budget_s / N_FRAMES)))
+    t0 = time.perf_counter()
+    n = oracle_step(sc, frames, n_pf, 1, t32, t64)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "rays/s", "cores": blas_threads(), "kind": "port",
+            "sample": f"{n} rays ({N_FRAMES} frames x {n_pf} px) of the {N_RAYS}-ray colour-stage mapping batch, "
+                      f"fwd+bwd, numpy oracle, {dt:.1f} s", "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import render_oracle as orc
+    scene, frames = make_inputs()
+    sc = orc.OracleScene.from_synthetic(scene)
+    t32 = torch.linspace(0., 1., 32).numpy()
+    t64 = torch.linspace(0., 1., 16).double().numpy()
+    t0 = time.perf_counter()
+    n = oracle_step(sc, frames, 10, 0, t32, t64)
+    rate = n / (time.perf_counter() - t0)
+    total = args.steps + args.warmup
+    n_pf = int(max(4, min(PIX_PER_FRAME, rate * (150.0 / max(total, 1)) / N_FRAMES)))
+    for w in range(args.warmup):
+        oracle_step(sc, frames, n_pf, 10 + w, t32, t64)
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(args.steps):
+        done += oracle_step(sc, frames, n_pf, 100 + k, t32, t64)
+    dt = time.perf_counter() - t0
+    val = done / dt
+    line = {
+        "impl": "reference", "metric": "rays/sec (fwd+bwd) on the Replica mapping batch", "value": val,
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 sample placement / depth sums)", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": blas_threads(), "kind": "port",
+                         "sample": f"{n_pf * N_FRAMES} rays per step of the {N_RAYS}-ray batch, numpy oracle port "
+                                   "of the reference renderer (the Python reference cannot travel to the GPU box)",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "Replica room0 mapping step, colour stage: 5 frames x 200 px = 1000 rays x (32 stratified + "
+                        "16 surface) samples, get_samples + render_batch_ray + Mapper loss + backward into grids "
+                        "(46 MiB, 3 levels), decoder weights and 4 BA camera tensors",
+            "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": S_TOTAL, "grids": "room0 [1,32,Z,Y,X] x 4 levels",
+            "decoders": "random-init NICE (pretrained blobs absent from the reference tree)",
+            "cache": "scene cache invalidated every step (grids re-laid-out and decoders re-packed inside the timed region)",
+            "l2": "flushed between timed steps (256 MiB write)", "sharding": "rays (weak): 1000 rays per GPU, "
+            "gradients SUM all-reduced"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from evennicer_slam_b200 import common, harness, sharding, functional, _lib
+    from evennicer_slam_b200.functional import TIMER
+
+    scene, frames = make_inputs()
+    decoders, c, renderer, cfg = harness.build(scene, dev)
+    cam = scene.cam
+    depth_t = [torch.from_numpy(d).to(dev) for (_, d, _) in frames]
+    color_t = [torch.from_numpy(col).to(dev) for (_, _, col) in frames]
+    cams = [torch.from_numpy(ct.copy()).to(dev) for (ct, _, _) in frames]
+    cam_params = [t.clone().requires_grad_(True) for t in cams[1:]]            # oldest frame fixed (Mapper.py:375)
+    grids = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    params = [p for p in decoders.parameters()]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.manual_seed(20 + rank)
+
+    def zero_grads():
+        for t in cam_params + list(grids.values()) + params:
+            t.grad = None
+
+    def step():
+        renderer._cache.invalidate()
+        ros, rds, sds, scs = [], [], [], []
+        for f in range(N_FRAMES):
+            ct = cams[0] if f == 0 else cam_params[f - 1]
+            c2w = common.get_camera_from_tensor(ct)
+            ro, rd, sd, sc_ = common.get_samples(0, cam.H, 0, cam.W, PIX_PER_FRAME, cam.H, cam.W, cam.fx, cam.fy,
+                                                 cam.cx, cam.cy, c2w, depth_t[f], color_t[f], dev)
+            ros.append(ro.float()); rds.append(rd.float()); sds.append(sd.float()); scs.append(sc_.float())
+        ro, rd, sd, sc_ = torch.cat(ros), torch.cat(rds), torch.cat(sds), torch.cat(scs)
+        depth, unc, color = renderer.render_batch_ray(grids, decoders, rd, ro, dev, "color", gt_depth=sd)
+        mask = sd > 0
+        loss = torch.abs(sd[mask] - depth[mask]).sum() + 0.2 * torch.abs(sc_ - color).sum()     # Mapper.py:553-562
+        loss.backward()
+        if world > 1:
+            sharding.allreduce_sum_([t.grad for t in list(grids.values()) + params + cam_params])
+        return loss
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        zero_grads(); step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    TIMER.reset(); TIMER.enabled = True
+    evs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        zero_grads()
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    TIMER.enabled = False
+    launches_timed = TIMER.launches
+    ksum = TIMER.summary()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * N_RAYS * args.steps / (dev_ms * 1e-3)
+
+    # ---- e2e: C-ABI-level call with host buffers (pinned), copies inside the timed region ----
+    e2e = measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world)
+
+    # ---- tracking iteration (config C2), reported beside the headline ----
+    track_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        n_b, t_b = ksum.get("render_bwd", (0, float("nan")))
+        n_f, t_f = ksum.get("render_fwd", (0, float("nan")))
+        achieved = BYTES_PER_POINT_BWD * N_RAYS * S_TOTAL / (t_b * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "render_bwd_kernel<color, wgrad>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
+                "peak_source": peak_src, "kernel_ms": t_b, "kernel_share_of_step": t_b / ms_per_step,
+                "fwd_kernel_ms": t_f, "fwd_achieved_gbs": BYTES_PER_POINT_FWD * N_RAYS * S_TOTAL / (t_f * 1e-3) / 1e9,
+                "step_algorithmic_gbs": BYTES_PER_RAY * N_RAYS / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": BYTES_PER_RAY * N_RAYS / (ms_per_step * 1e-3) / 1e9 / peak}
+        cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        line = {
+            "metric": "rays/sec (fwd+bwd) on the Replica mapping batch", "value": value, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 sample placement / depth sums)", "data": "synthetic",
+            "config": workload_config(), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches_timed, "gpu_launches_per_step": launches_timed / args.steps,
+            "roofline": roof, "cpu_baseline": cpu,
+            "tracking_ms_per_iter": track_ms, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("render_bwd_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world):
+    """Host-buffer call: pinned rays/depth/colour in, depth/var/colour + ray gradients + loss out."""
+    import torch
+    import render_oracle as orc
+    import evennicer_slam_b200.synthetic as syn
+    cam = scene.cam
+    rng = np.random.RandomState(7)
+    ros, rds, sds, scs = [], [], [], []
+    for (cam_t, depth, color) in frames:
+        idx = rng.randint(0, cam.H * cam.W, size=PIX_PER_FRAME)
+        i, j, sd, scol = orc.select_pixels(idx, 0, cam.H, 0, cam.W, depth, color)
+        ro, rd = orc.rays_from_uv(i, j, syn.quat_to_c2w(cam_t), cam.fx, cam.fy, cam.cx, cam.cy)
+        ros.append(ro); rds.append(rd); sds.append(sd); scs.append(scol.astype(np.float32))
+    h_in = [torch.from_numpy(np.concatenate(x)).pin_memory() for x in (ros, rds, sds, scs)]
+    h2d = sum(t.numel() * t.element_size() for t in h_in)
+    h_out = {"depth": torch.empty(N_RAYS, dtype=torch.float64).pin_memory(),
+             "var": torch.empty(N_RAYS, dtype=torch.float64).pin_memory(),
+             "color": torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory(),
+             "g_ro": torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory(),
+             "g_rd": torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory(),
+             "loss": torch.empty(1, dtype=torch.float64).pin_memory()}
+    d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+    params = list(decoders.parameters())
+
+    def step():
+        renderer._cache.invalidate()
+        for t in list(grids.values()) + params:
+            t.grad = None
+        ro, rd, sd, sc_ = [t.to(dev, non_blocking=True) for t in h_in]
+        ro.requires_grad_(True); rd.requires_grad_(True)
+        depth, unc, color = renderer.render_batch_ray(grids, decoders, rd, ro, dev, "color", gt_depth=sd)
+        mask = sd > 0
+        loss = torch.abs(sd[mask] - depth[mask]).sum() + 0.2 * torch.abs(sc_ - color).sum()
+        loss.backward()
+        h_out["depth"].copy_(depth.detach(), non_blocking=True)
+        h_out["var"].copy_(unc.detach(), non_blocking=True)
+        h_out["color"].copy_(color.detach(), non_blocking=True)
+        h_out["g_ro"].copy_(ro.grad, non_blocking=True)
+        h_out["g_rd"].copy_(rd.grad, non_blocking=True)
+        h_out["loss"].copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"value": world * N_RAYS * args.steps / float(t.item()), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "timing": "host wall clock around K synchronous steps (copies + sync inside)"}
+
+
+def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20):
+    """Config C2: 200 px from the crop [100:580, 100:1100], colour stage, pose gradient only (Tracker.py:159-197)."""
+    import torch
+    from evennicer_slam_b200 import common
+    cam = scene.cam
+    cam_t, depth, color = frames[-1]
+    depth_t = torch.from_numpy(depth).to(dev)
+    color_t = torch.from_numpy(color).to(dev)
+    ct = torch.from_numpy(cam_t.copy()).to(dev).requires_grad_(True)
+    req = [p.requires_grad for p in decoders.parameters()]
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+
+    def it():
+        ct.grad = None
+        c2w = common.get_camera_from_tensor(ct)
+        ro, rd, sd, sc_ = common.get_samples(100, cam.H - 100, 100, cam.W - 100, 200, cam.H, cam.W, cam.fx, cam.fy,
+                                             cam.cx, cam.cy, c2w, depth_t, color_t, dev)
+        d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, dev, "color", gt_depth=sd)
+        u = u.detach()
+        tmp = torch.abs(sd - d) / torch.sqrt(u + 1e-10)
+        mask = (tmp < 10 * tmp.median()) & (sd > 0)
+        loss = (torch.abs(sd - d) / torch.sqrt(u + 1e-10))[mask].sum() + 0.5 * torch.abs(sc_ - col)[mask].sum()
+        loss.backward()
+
+    for _ in range(3):
+        it()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); it(); b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    for p, r in zip(decoders.parameters(), req):
+        p.requires_grad_(r)
+    return tot / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

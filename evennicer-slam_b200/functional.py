@@ -15,6 +15,42 @@ from ._lib import LEVELS, STAGES, STAGE_LEVELS, EnsGrads, EnsRenderCfg
 from .scene import SceneCache, build_scene_struct, decoder_grad_views
 
 
+_DEBUG: Dict[str, object] = {}     # test hook: set _DEBUG["keep_workspace"]=True to inspect the backward scratch
+
+
+class KernelTimer:
+    """CUDA-event timing of individual C-ABI launches on the launching stream (bench.py uses it to get the
+    dominant kernel's duration inside the timed region).  Also counts launches."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+        self.launches = 0
+
+    def reset(self):
+        self.events = {}
+        self.launches = 0
+
+    def launch(self, name, device, fn):
+        self.launches += 1
+        if not self.enabled:
+            return fn()
+        s = torch.cuda.current_stream(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(s)
+        rc = fn()
+        b.record(s)
+        self.events.setdefault(name, []).append((a, b))
+        return rc
+
+    def summary(self):
+        """name -> (count, mean ms); call after a synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in self.events.items()}
+
+
+TIMER = KernelTimer()
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -59,6 +95,7 @@ def depth_batch_max(gt_depth: torch.Tensor) -> torch.Tensor:
     """device double[2] = (max(gt_depth*1.2), max(gt_depth))  -- Renderer.py:110,145."""
     out = torch.empty(2, dtype=torch.float64, device=gt_depth.device)
     L = _lib.lib()
+    TIMER.launches += 1
     _lib.check(L.ens_depth_max(_lib.ptr(gt_depth), gt_depth.numel(), _lib.ptr(out),
                                _lib.cur_stream(gt_depth.device)), "ens_depth_max")
     return out
@@ -98,10 +135,11 @@ class _RenderBatchRay(torch.autograd.Function):
         z = torch.empty((R, S), dtype=torch.float64, device=dev) if want_aux else None
         w = torch.empty((R, S), dtype=torch.float32, device=dev) if want_aux else None
         gd = _f32c(gt_depth).reshape(-1) if has_depth else None
-        _lib.check(L.ens_render_fwd(C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd),
-                                    _lib.ptr(gd), _lib.ptr(depth_max) if has_depth else None, R,
-                                    _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(z), _lib.ptr(w),
-                                    _lib.ptr(raw), _lib.cur_stream(dev)), "ens_render_fwd")
+        stream = _lib.cur_stream(dev)
+        _lib.check(TIMER.launch("render_fwd", dev, lambda: L.ens_render_fwd(
+            C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd),
+            _lib.ptr(depth_max) if has_depth else None, R, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color),
+            _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), stream)), "ens_render_fwd")
         ctx.setup = setup
         ctx.levels = levels
         ctx.n_grids = n_grids
@@ -112,10 +150,10 @@ class _RenderBatchRay(torch.autograd.Function):
         ctx.param_shapes = {lv: per_level_params[lv] for lv in levels}
         ctx.save_for_backward(ro, rd, gd if gd is not None else torch.empty(0, device=dev),
                               depth_max if has_depth else torch.empty(0, device=dev), raw)
-        ctx.mark_non_differentiable(raw)
         if want_aux:
-            ctx.mark_non_differentiable(z, w)
+            ctx.mark_non_differentiable(raw, z, w)
             return depth, var, color, raw, z, w
+        ctx.mark_non_differentiable(raw)
         return depth, var, color, raw
 
     @staticmethod
@@ -161,11 +199,14 @@ class _RenderBatchRay(torch.autograd.Function):
         gdp = g_depth.detach().to(torch.float64).contiguous() if g_depth is not None else None
         gvp = g_var.detach().to(torch.float64).contiguous() if g_var is not None else None
         gcp = _f32c(g_color) if g_color is not None else None
-        _lib.check(L.ens_render_bwd(C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd),
-                                    _lib.ptr(gd) if ctx.has_depth else None,
-                                    _lib.ptr(depth_max) if ctx.has_depth else None, R, _lib.ptr(raw),
-                                    _lib.ptr(gdp), _lib.ptr(gvp), _lib.ptr(gcp), C.byref(grads), _lib.ptr(ws),
-                                    ws_bytes, _lib.cur_stream(dev)), "ens_render_bwd")
+        stream = _lib.cur_stream(dev)
+        _lib.check(TIMER.launch("render_bwd", dev, lambda: L.ens_render_bwd(
+            C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd),
+            _lib.ptr(gd) if ctx.has_depth else None, _lib.ptr(depth_max) if ctx.has_depth else None, R,
+            _lib.ptr(raw), _lib.ptr(gdp), _lib.ptr(gvp), _lib.ptr(gcp), C.byref(grads), _lib.ptr(ws), ws_bytes,
+            stream)), "ens_render_bwd")
+        if _DEBUG.get("keep_workspace"):
+            _DEBUG["workspace"] = ws
         out: List[Optional[torch.Tensor]] = [None] * 6
         out.append(g_ro if need_ro else None)
         out.append(g_rd if need_rd else None)
@@ -174,6 +215,7 @@ class _RenderBatchRay(torch.autograd.Function):
                 nat = g_native[lv]
                 Z, Y, X = nat.shape[:3]
                 g_ref = torch.empty((1, 32, Z, Y, X), dtype=torch.float32, device=dev)
+                TIMER.launches += 1
                 _lib.check(L.ens_grid_from_native(_lib.ptr(nat), _lib.ptr(g_ref), Z * Y * X, 0,
                                                   _lib.cur_stream(dev)), "ens_grid_from_native")
                 out.append(g_ref)
@@ -193,7 +235,7 @@ class _RenderBatchRay(torch.autograd.Function):
 
 
 def render_batch_ray(setup: RenderSetup, c: Dict[str, torch.Tensor], decoders, rays_d, rays_o, gt_depth=None,
-                     want_aux: bool = False):
+                     want_aux: bool = False, depth_max: Optional[torch.Tensor] = None):
     """Fused Renderer.render_batch_ray.  Returns (depth f64, var f64, color f32[, raw, z_vals, weights])."""
     from .scene import decoder_tensors
     levels = STAGE_LEVELS[setup.stage]
@@ -202,12 +244,14 @@ def render_batch_ray(setup: RenderSetup, c: Dict[str, torch.Tensor], decoders, r
     for lv in levels:
         params.extend(decoder_tensors(decoders, lv))
     has_depth = gt_depth is not None and setup.stage != "coarse"
-    depth_max = None
     if has_depth:
         gt_depth = gt_depth.reshape(-1)
         if gt_depth.dtype != torch.float32:
             gt_depth = gt_depth.float()
-        depth_max = depth_batch_max(gt_depth.contiguous())
+        if depth_max is None:       # sharded callers pass the maxima of the WHOLE batch (sharding.py)
+            depth_max = depth_batch_max(gt_depth.contiguous())
+    else:
+        depth_max = None
     out = _RenderBatchRay.apply(setup, gt_depth if has_depth else None, depth_max, len(grids), levels, want_aux,
                                 rays_o, rays_d, *grids, *params)
     if want_aux:
@@ -231,6 +275,7 @@ def eval_points(setup: RenderSetup, c, decoders, p: torch.Tensor, apply_mask: bo
     p = p.contiguous()
     n = p.shape[0]
     out = torch.empty((n, 4), dtype=torch.float32, device=p.device)
+    TIMER.launches += 1
     _lib.check(L.ens_eval_points(C.byref(sc), STAGES[setup.stage], _lib.ptr(p), int(p.dtype == torch.float64), n,
                                  int(apply_mask), _lib.ptr(out), _lib.cur_stream(p.device)), "ens_eval_points")
     return out
@@ -268,6 +313,7 @@ class _SampleRays(torch.autograd.Function):
         col = color if color.is_contiguous() else color.contiguous()
         if col.dtype not in (torch.float32, torch.float64):
             raise ValueError("color must be float32 or float64")
+        TIMER.launches += 1
         _lib.check(L.ens_sample_rays(_lib.ptr(indices), n, H0, H1, W0, W1, H, W, fx, fy, cx, cy, _lib.ptr(m),
                                      m.stride(0), _lib.ptr(dep), _lib.ptr(col), int(is64), _lib.ptr(pi),
                                      _lib.ptr(pj), _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(sd), _lib.ptr(sc),
@@ -287,6 +333,7 @@ class _SampleRays(torch.autograd.Function):
         g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
         gro = _f32c(g_ro) if g_ro is not None else None
         grd = _f32c(g_rd) if g_rd is not None else None
+        TIMER.launches += 1
         _lib.check(L.ens_rays_bwd(_lib.ptr(pi), _lib.ptr(pj), pi.numel(), 0, fx, fy, cx, cy, _lib.ptr(gro),
                                   _lib.ptr(grd), _lib.ptr(g), _lib.cur_stream(dev)), "ens_rays_bwd")
         if ctx.c2w_shape[0] == 4:
@@ -306,6 +353,7 @@ class _LatticeRays(torch.autograd.Function):
         m = _f32c(c2w)
         ro = torch.empty((nH, nW, 3), dtype=torch.float32, device=dev)
         rd = torch.empty((nH, nW, 3), dtype=torch.float32, device=dev)
+        TIMER.launches += 1
         _lib.check(L.ens_lattice_rays(_lib.ptr(lin_w), nW, _lib.ptr(lin_h), nH, fx, fy, cx, cy, _lib.ptr(m),
                                       m.stride(0), _lib.ptr(ro), _lib.ptr(rd), _lib.cur_stream(dev)),
                    "ens_lattice_rays")
@@ -324,6 +372,7 @@ class _LatticeRays(torch.autograd.Function):
         g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
         gro = _f32c(g_ro).reshape(-1, 3) if g_ro is not None else None
         grd = _f32c(g_rd).reshape(-1, 3) if g_rd is not None else None
+        TIMER.launches += 1
         _lib.check(L.ens_rays_bwd(_lib.ptr(lin_w), _lib.ptr(lin_h), n, lin_w.numel(), fx, fy, cx, cy,
                                   _lib.ptr(gro), _lib.ptr(grd), _lib.ptr(g), _lib.cur_stream(dev)), "ens_rays_bwd")
         if ctx.c2w_shape[0] == 4:
@@ -343,6 +392,7 @@ class _PairRays(torch.autograd.Function):
         m = _f32c(c2w)
         ro = torch.empty((n, 3), dtype=torch.float32, device=dev)
         rd = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        TIMER.launches += 1
         _lib.check(L.ens_lattice_rays(_lib.ptr(pix_i), n, _lib.ptr(pix_j), 0, fx, fy, cx, cy, _lib.ptr(m),
                                       m.stride(0), _lib.ptr(ro), _lib.ptr(rd), _lib.cur_stream(dev)),
                    "ens_lattice_rays")
@@ -360,6 +410,7 @@ class _PairRays(torch.autograd.Function):
         g = torch.zeros((3, 4), dtype=torch.float32, device=dev)
         gro = _f32c(g_ro) if g_ro is not None else None
         grd = _f32c(g_rd) if g_rd is not None else None
+        TIMER.launches += 1
         _lib.check(L.ens_rays_bwd(_lib.ptr(pi), _lib.ptr(pj), pi.numel(), 0, fx, fy, cx, cy, _lib.ptr(gro),
                                   _lib.ptr(grd), _lib.ptr(g), _lib.cur_stream(dev)), "ens_rays_bwd")
         if ctx.c2w_shape[0] == 4:

@@ -58,6 +58,13 @@ class SceneCache:
         self._decs: Dict[Tuple[str, int], _DecEntry] = {}
         self.stats = {"grid_convert": 0, "grid_hit": 0, "dec_pack": 0, "dec_hit": 0}
 
+    def invalidate(self, grids: bool = True, decoders: bool = True):
+        """Forget cached layouts (bench: model a scene that was mutated since the last call)."""
+        if grids:
+            self._grids.clear()
+        if decoders:
+            self._decs.clear()
+
     # -- grids ---------------------------------------------------------------------------
     def native_grid(self, level: str, grid: torch.Tensor) -> torch.Tensor:
         if grid.dim() != 5 or grid.shape[0] != 1 or grid.shape[1] != 32:
@@ -76,6 +83,8 @@ class SceneCache:
         # always a fresh buffer: an earlier forward may still hold the old one for its backward
         native = torch.empty((Z, Y, X, 32), dtype=torch.float32, device=grid.device)
         L = _lib.lib()
+        from .functional import TIMER
+        TIMER.launches += 1
         _lib.check(L.ens_grid_to_native(_lib.ptr(src), _lib.ptr(native), Z * Y * X,
                                         _lib.cur_stream(grid.device)), "ens_grid_to_native")
         e = _GridEntry()
@@ -109,6 +118,8 @@ class SceneCache:
             keep.append(t)
             arr[i] = t.data_ptr()
         packed = torch.empty(int(L.ens_packed_decoder_floats(li)), dtype=torch.float32, device=dev)
+        from .functional import TIMER
+        TIMER.launches += 1
         _lib.check(L.ens_pack_decoder(li, arr, n, _lib.ptr(packed), _lib.cur_stream(dev)), "ens_pack_decoder")
         e = _DecEntry()
         e.refs = [weakref.ref(p) for p in params]

@@ -1,0 +1,119 @@
+"""Ray / point sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+The render path shards by independent units (rays, lattice points); SURVEY.md 8(e).  The only
+cross-ray coupling inside ``render_batch_ray`` is the pair of batch maxima of ``gt_depth``
+(Renderer.py:110,145), recovered exactly with one MAX all-reduce of two doubles.  Exchanges:
+
+  full-frame render / mesh lattice : all-gather of per-ray (per-point) outputs, 28 (16) bytes each
+  mapping step                     : SUM all-reduce of grid / decoder / pose gradients (replicated scene)
+  tracking 200 px                  : replicas only (no collective)
+
+NCCL over NVLink on the GPU box; the same code runs on gloo/CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of n units for `rank` (first n % world ranks get one more)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def global_depth_max(local: torch.Tensor, group=None) -> torch.Tensor:
+    """MAX all-reduce of the (max(gt*1.2), max(gt)) pair so every shard places samples as the whole batch would."""
+    if world(group)[1] > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.MAX, group=group)
+    return local
+
+
+def allreduce_sum_(tensors: Sequence[Optional[torch.Tensor]], group=None, bucket_bytes: int = 256 << 20) -> None:
+    """In-place SUM all-reduce of gradient tensors, coalesced into flat buckets (one collective per bucket)."""
+    if world(group)[1] == 1:
+        return
+    todo = [t for t in tensors if t is not None]
+    by_key = {}
+    for t in todo:
+        by_key.setdefault((t.dtype, t.device), []).append(t)
+    for (_, _), ts in by_key.items():
+        bucket: List[torch.Tensor] = []
+        size = 0
+        for t in ts + [None]:
+            if t is not None and (size + t.numel() * t.element_size() <= bucket_bytes or not bucket):
+                bucket.append(t)
+                size += t.numel() * t.element_size()
+                continue
+            flat = torch.cat([b.reshape(-1) for b in bucket]) if len(bucket) > 1 else bucket[0].reshape(-1)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if len(bucket) > 1 or not bucket[0].is_contiguous():
+                off = 0
+                for b in bucket:
+                    b.copy_(flat[off:off + b.numel()].view_as(b))
+                    off += b.numel()
+            bucket, size = ([t], t.numel() * t.element_size()) if t is not None else ([], 0)
+
+
+def allgather_rows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """Concatenate per-rank row blocks (rank r holds counts[r] rows) on every rank."""
+    r, w = world(group)
+    if w == 1:
+        return local
+    mx = max(counts)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    out = [torch.empty_like(pad) for _ in range(w)]
+    dist.all_gather(out, pad.contiguous(), group=group)
+    return torch.cat([o[:n] for o, n in zip(out, counts)], 0)
+
+
+def render_rays_sharded(renderer, c, decoders, rays_d, rays_o, device, stage, gt_depth=None, group=None):
+    """render_batch_ray of ONE reference batch, rays split over the ranks; every rank gets all outputs.
+
+    Identical to the unsharded result: the depth maxima are reduced over the whole batch first.
+    """
+    from .functional import depth_batch_max, render_batch_ray as _rbr
+    r, w = world(group)
+    n = rays_o.shape[0]
+    lo, hi = shard_range(n, r, w)
+    dmax = None
+    gd = None
+    if gt_depth is not None and stage != "coarse":
+        gd = gt_depth.reshape(-1).float()
+        if hi > lo:
+            dmax = depth_batch_max(gd[lo:hi].contiguous())
+        else:
+            dmax = torch.full((2,), float("-inf"), dtype=torch.float64, device=rays_o.device)
+        dmax = global_depth_max(dmax, group)
+        gd = gd[lo:hi]
+    setup = renderer._setup(stage, decoders, rays_o.device)
+    if hi > lo:
+        depth, var, color = _rbr(setup, c, decoders, rays_d[lo:hi], rays_o[lo:hi], gd, depth_max=dmax)
+    else:
+        depth = torch.empty(0, dtype=torch.float64, device=rays_o.device)
+        var = torch.empty(0, dtype=torch.float64, device=rays_o.device)
+        color = torch.empty((0, 3), dtype=torch.float32, device=rays_o.device)
+    counts = [shard_range(n, q, w)[1] - shard_range(n, q, w)[0] for q in range(w)]
+    return (allgather_rows(depth, counts, group), allgather_rows(var, counts, group),
+            allgather_rows(color, counts, group))
+
+
+def eval_points_sharded(renderer, p, decoders, c, stage, device, group=None):
+    """Renderer.eval_points over a point lattice split across ranks (mesh extraction, config 5)."""
+    r, w = world(group)
+    n = p.shape[0]
+    lo, hi = shard_range(n, r, w)
+    local = renderer.eval_points(p[lo:hi], decoders, c, stage, device)
+    counts = [shard_range(n, q, w)[1] - shard_range(n, q, w)[0] for q in range(w)]
+    return allgather_rows(local, counts, group)

@@ -13,7 +13,10 @@ import evennicer_slam_b200.synthetic as syn
 SEED = 20                      # run.py:11-20 -- the authors' own setup_seed(20)
 N_TINY_RAYS = 96
 N_ROOM0_RAYS = 1000
-TINY_STD = {"coarse": 0.05, "middle": 0.05, "fine": 0.05, "color": 0.05}
+# Coarse features are larger: with tiny features the coarse decoder is bias-driven, pre-activations
+# barely vary across points and a whole unit can sit within float rounding of the relu boundary, where
+# CPU and GPU legitimately disagree on the mask (make_golden.py asserts a margin for every decoder).
+TINY_STD = {"coarse": 0.5, "middle": 0.05, "fine": 0.05, "color": 0.05}
 
 
 def tiny_scene():

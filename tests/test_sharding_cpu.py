@@ -1,0 +1,66 @@
+"""world_size-2 gloo tests of the host-side sharding logic (no GPU)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from evennicer_slam_b200 import sharding as sh
+    try:
+        # depth maxima: MAX over shards == max of the whole batch
+        full = torch.arange(11, dtype=torch.float32) * 0.37
+        lo, hi = sh.shard_range(11, rank, world)
+        local = torch.tensor([float(full[lo:hi].max() * 1.2), float(full[lo:hi].max())], dtype=torch.float64)
+        g = sh.global_depth_max(local)
+        assert g[1].item() == float(full.max()) and g[0].item() == float(full.max() * 1.2)
+        # gradient all-reduce, several tensors / dtypes, bucketed
+        a = torch.full((5, 3), float(rank + 1))
+        b = torch.full((7,), float(10 * (rank + 1)), dtype=torch.float64)
+        c = torch.full((2, 2), float(rank))
+        sh.allreduce_sum_([a, None, b, c], bucket_bytes=64)
+        tot = sum(range(1, world + 1))
+        assert torch.all(a == tot) and torch.all(b == 10 * tot) and torch.all(c == sum(range(world)))
+        # ragged all-gather
+        rows = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
+        counts = [sh.shard_range(11, r, world)[1] - sh.shard_range(11, r, world)[0] for r in range(world)]
+        allr = sh.allgather_rows(rows, counts)
+        assert torch.equal(allr[:, 0], torch.arange(11, dtype=torch.float32))
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    from evennicer_slam_b200.sharding import shard_range
+    for n in (0, 1, 7, 100000, 816000):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_collectives_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] == "ok" for r in res), res
