@@ -59,6 +59,8 @@ _SIGNATURES = {
                                    C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ens_rays_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ens_pose_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ens_pose_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ens_eval_points": (C.c_int, [C.POINTER(EnsScene), C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     "ens_render_fwd": (C.c_int, [C.POINTER(EnsScene), C.POINTER(EnsRenderCfg), C.c_int, C.c_void_p, C.c_void_p,

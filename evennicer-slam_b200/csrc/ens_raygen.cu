@@ -101,9 +101,70 @@ __global__ void __launch_bounds__(256) rays_bwd_kernel(const float *__restrict__
   }
 }
 
+// quad2rotation + get_camera_from_tensor (common.py:189-228) for n camera tensors [qw,qx,qy,qz,tx,ty,tz],
+// and its backward.  One thread per camera; float32 with the reference's expression order.
+__global__ void pose_fwd_kernel(const float *__restrict__ cam, int n, float *__restrict__ c2w) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float qr = cam[t * 7 + 0], qi = cam[t * 7 + 1], qj = cam[t * 7 + 2], qk = cam[t * 7 + 3];
+  const float nn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qr, qr), __fmul_rn(qi, qi)), __fmul_rn(qj, qj)), __fmul_rn(qk, qk));
+  const float s = __fdiv_rn(2.0f, nn);
+  float *o = c2w + t * 12;
+  o[0] = __fsub_rn(1.f, __fmul_rn(s, __fadd_rn(__fmul_rn(qj, qj), __fmul_rn(qk, qk))));
+  o[1] = __fmul_rn(s, __fsub_rn(__fmul_rn(qi, qj), __fmul_rn(qk, qr)));
+  o[2] = __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qk), __fmul_rn(qj, qr)));
+  o[3] = cam[t * 7 + 4];
+  o[4] = __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qj), __fmul_rn(qk, qr)));
+  o[5] = __fsub_rn(1.f, __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qi), __fmul_rn(qk, qk))));
+  o[6] = __fmul_rn(s, __fsub_rn(__fmul_rn(qj, qk), __fmul_rn(qi, qr)));
+  o[7] = cam[t * 7 + 5];
+  o[8] = __fmul_rn(s, __fsub_rn(__fmul_rn(qi, qk), __fmul_rn(qj, qr)));
+  o[9] = __fmul_rn(s, __fadd_rn(__fmul_rn(qj, qk), __fmul_rn(qi, qr)));
+  o[10] = __fsub_rn(1.f, __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qi), __fmul_rn(qj, qj))));
+  o[11] = cam[t * 7 + 6];
+}
+
+__global__ void pose_bwd_kernel(const float *__restrict__ cam, int n, const float *__restrict__ g, float *__restrict__ gcam) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float qr = cam[t * 7 + 0], qi = cam[t * 7 + 1], qj = cam[t * 7 + 2], qk = cam[t * 7 + 3];
+  const float nn = qr * qr + qi * qi + qj * qj + qk * qk;
+  const float s = 2.0f / nn;
+  const float *G = g + t * 12;
+  // R = I*[1..] + s*M(q): dL/ds = sum G_ab * M_ab ; dL/dq = s * dM/dq contributions + dL/ds * ds/dq, ds/dq = -s^2 q... (= -2*2q/nn^2)
+  const float m00 = -(qj * qj + qk * qk), m01 = qi * qj - qk * qr, m02 = qi * qk + qj * qr;
+  const float m10 = qi * qj + qk * qr, m11 = -(qi * qi + qk * qk), m12 = qj * qk - qi * qr;
+  const float m20 = qi * qk - qj * qr, m21 = qj * qk + qi * qr, m22 = -(qi * qi + qj * qj);
+  const float gs = G[0] * m00 + G[1] * m01 + G[2] * m02 + G[4] * m10 + G[5] * m11 + G[6] * m12 + G[8] * m20 + G[9] * m21 + G[10] * m22;
+  const float dsdq = -s * s;       // ds/dq_x = -2*2*q_x/nn^2 = -(s^2) * q_x
+  float gr = s * (-G[1] * qk + G[2] * qj + G[4] * qk - G[6] * qi - G[8] * qj + G[9] * qi);
+  float gi = s * (G[1] * qj + G[2] * qk + G[4] * qj - 2.f * G[5] * qi - G[6] * qr + G[8] * qk + G[9] * qr - 2.f * G[10] * qi);
+  float gj = s * (-2.f * G[0] * qj + G[1] * qi + G[2] * qr + G[4] * qi + G[6] * qk - G[8] * qr + G[9] * qk - 2.f * G[10] * qj);
+  float gk = s * (-2.f * G[0] * qk - G[1] * qr + G[2] * qi + G[4] * qr - 2.f * G[5] * qk + G[6] * qj + G[8] * qi + G[9] * qj);
+  gr += gs * dsdq * qr; gi += gs * dsdq * qi; gj += gs * dsdq * qj; gk += gs * dsdq * qk;
+  float *o = gcam + t * 7;
+  o[0] = gr; o[1] = gi; o[2] = gj; o[3] = gk; o[4] = G[3]; o[5] = G[7]; o[6] = G[11];
+}
+
 }  // namespace ens
 
 using namespace ens;
+
+extern "C" int ens_pose_fwd(const float *cam_tensors, int n, float *c2w, ens_stream_t stream) {
+  if (!cam_tensors || !c2w || n < 0) return ENS_EINVAL;
+  if (n == 0) return ENS_OK;
+  pose_fwd_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(cam_tensors, n, c2w);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+extern "C" int ens_pose_bwd(const float *cam_tensors, int n, const float *g_c2w, float *g_cam, ens_stream_t stream) {
+  if (!cam_tensors || !g_c2w || !g_cam || n < 0) return ENS_EINVAL;
+  if (n == 0) return ENS_OK;
+  pose_bwd_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(cam_tensors, n, g_c2w, g_cam);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
 
 extern "C" int ens_sample_rays(const int64_t *indices, int64_t n, int H0, int H1, int W0, int W1, int H, int W,
                                float fx, float fy, float cx, float cy, const float *c2w, int c2w_stride,

@@ -416,3 +416,29 @@ class _PairRays(torch.autograd.Function):
         if ctx.c2w_shape[0] == 4:
             g = torch.cat([g, torch.zeros((1, 4), dtype=torch.float32, device=dev)], 0)
         return g, None, None, None
+
+
+class _PoseToC2W(torch.autograd.Function):
+    """get_camera_from_tensor (common.py:215-228) for (n,7) camera tensors: one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, cam):
+        L = _lib.lib()
+        x = _f32c(cam)
+        n = x.shape[0]
+        out = torch.empty((n, 3, 4), dtype=torch.float32, device=x.device)
+        TIMER.launches += 1
+        _lib.check(L.ens_pose_fwd(_lib.ptr(x), n, _lib.ptr(out), _lib.cur_stream(x.device)), "ens_pose_fwd")
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        (x,) = ctx.saved_tensors
+        n = x.shape[0]
+        gc = torch.empty((n, 7), dtype=torch.float32, device=x.device)
+        TIMER.launches += 1
+        _lib.check(L.ens_pose_bwd(_lib.ptr(x), n, _lib.ptr(_f32c(g)), _lib.ptr(gc), _lib.cur_stream(x.device)),
+                   "ens_pose_bwd")
+        return gc

@@ -135,6 +135,12 @@ int ens_rays_bwd(const float *pix_i, const float *pix_j, int64_t n, int nW, floa
                  float cy, const float *g_rays_o, const float *g_rays_d, float *g_c2w,
                  ens_stream_t stream);
 
+/* common.get_camera_from_tensor / quad2rotation (src/common.py:189-228): n camera tensors
+ * [qw,qx,qy,qz,tx,ty,tz] (un-normalised quaternion allowed) -> n x [3][4] float32 [R|t]; and the
+ * backward g_c2w [n][3][4] -> g_cam [n][7] (written).  In eager PyTorch this is ~60 tiny kernels per pose. */
+int ens_pose_fwd(const float *cam_tensors, int n, float *c2w, ens_stream_t stream);
+int ens_pose_bwd(const float *cam_tensors, int n, const float *g_c2w, float *g_cam, ens_stream_t stream);
+
 /* Renderer.eval_points (src/utils/Renderer.py:24-62; clone at src/utils/Mesher.py:281-319):
  * pts [N][3] float64 or float32 -> out [N][4] float32 (r,g,b,occ).  apply_bound_mask != 0 applies the
  * `ret[~mask,3] = 100` rule for points outside slam.bound (Renderer.py:43-58); 0 gives the bare
