@@ -50,6 +50,37 @@ struct MlpPack {
   __host__ __device__ static constexpr int total() { return off_bo() + 4; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Packed decoder blob, "mma" layout (tensor-core variant).  Matrices are stored as PyTorch keeps them,
+// [out=32][in] with the input index contiguous, DENSE (no padding) and XOR-swizzled so that the
+// m16n8k8 B-fragment loads (one 8-byte load of W[n][8kt+2t .. +1] per lane) are bank-conflict free:
+//     element (n, k) of a [32][W] matrix lives at  n*W + (k ^ ((n & 3) << 3)).
+//   B      [3][96]
+//   W0     [32][96]   pts_linears.0.weight, k padded 93 -> 96 with zeros
+//   W3e    [32][96]   pts_linears.3.weight[:, 0:93]   (embedding half of the skip layer)
+//   block i=0..4:  Wh_i [32][32] (i=1,2,4: pts_linears.i.weight; i=3: pts_linears.3.weight[:, 93:125]; i=0: zeros)
+//                  b_i  [32]     pts_linears.i.bias
+//                  Wc_i [32][CD] fc_c.i.weight
+//                  bc_i [32]     fc_c.i.bias
+//   Wo     [4][32] output_linear.weight (rows >= NO zero), bo [4]
+// ---------------------------------------------------------------------------------------------
+template <int CD>
+struct MlpPackV2 {
+  __host__ __device__ static constexpr int off_B() { return 0; }
+  __host__ __device__ static constexpr int off_W0() { return 3 * EMBP; }
+  __host__ __device__ static constexpr int off_W3e() { return off_W0() + 32 * EMBP; }
+  __host__ __device__ static constexpr int block_floats() { return 32 * 32 + 32 + 32 * CD + 32; }
+  __host__ __device__ static constexpr int off_L(int i) { return off_W3e() + 32 * EMBP + i * block_floats(); }
+  __host__ __device__ static constexpr int in_Wh() { return 0; }
+  __host__ __device__ static constexpr int in_b() { return 32 * 32; }
+  __host__ __device__ static constexpr int in_Wc() { return 32 * 32 + 32; }
+  __host__ __device__ static constexpr int in_bc() { return 32 * 32 + 32 + 32 * CD; }
+  __host__ __device__ static constexpr int off_Wo() { return off_L(5); }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int total() { return off_bo() + 4; }
+};
+__host__ __device__ constexpr int swz(int row, int k) { return k ^ ((row & 3) << 3); }
+
 struct CoarsePack {
   __host__ __device__ static constexpr int K(int i) { return i == 3 ? 64 : 32; }
   __host__ __device__ static constexpr int off_W(int i) {
@@ -98,11 +129,12 @@ struct CoarseGrad {
   __host__ __device__ static constexpr int total() { return off_bo() + 1; }
 };
 
+// A packed blob holds the fma layout followed by the mma layout (coarse: fma only).
 __host__ __device__ inline int packed_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarsePack::total();
-    case ENS_LEVEL_FINE: return MlpPack<64>::total();
-    default: return MlpPack<32>::total();
+    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total();
+    default: return MlpPack<32>::total() + MlpPackV2<32>::total();
   }
 }
 __host__ __device__ inline int grad_floats(int level) {

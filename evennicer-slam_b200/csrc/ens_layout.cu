@@ -92,6 +92,51 @@ __global__ void pack_mlp_kernel(PtrTable t, float *__restrict__ out) {
   out[idx] = v;
 }
 
+// mma layout (see MlpPackV2): dense [out][in], XOR-swizzled columns
+template <int CD, int NO>
+__global__ void pack_mlp_v2_kernel(PtrTable t, float *__restrict__ out) {
+  using P = MlpPackV2<CD>;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P::total()) return;
+  float v = 0.f;
+  if (idx < P::off_W0()) {
+    int r = idx / EMBP, k = idx % EMBP;
+    v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f;
+  } else if (idx < P::off_L(0)) {
+    const bool is3 = idx >= P::off_W3e();
+    int o = idx - (is3 ? P::off_W3e() : P::off_W0());
+    int n = o / EMBP, k = swz(n, o % EMBP);           // physical column -> logical k (swz is an involution)
+    if (k < EMB) v = is3 ? t.p[11 + 2 * 3][n * 125 + k] : t.p[11][n * EMB + k];
+  } else if (idx < P::off_Wo()) {
+    int o = idx - P::off_L(0);
+    const int i = o / P::block_floats();
+    o -= i * P::block_floats();
+    if (o < P::in_b()) {
+      int n = o / 32, k = swz(n, o % 32);
+      if (i == 3) v = t.p[11 + 2 * 3][n * 125 + EMB + k];
+      else if (i > 0) v = t.p[11 + 2 * i][n * 32 + k];
+    } else if (o < P::in_Wc()) {
+      v = t.p[12 + 2 * i][o - P::in_b()];
+    } else if (o < P::in_bc()) {
+      int q = o - P::in_Wc();
+      int n = q / CD, k = swz(n, q % CD);
+      v = t.p[2 * i][n * CD + k];
+    } else {
+      v = t.p[2 * i + 1][o - P::in_bc()];
+    }
+  } else {
+    int o = idx - P::off_Wo();
+    if (o < 128) {
+      int n = o / 32, j = o % 32;
+      v = (n < NO) ? t.p[21][n * 32 + j] : 0.f;
+    } else {
+      int n = o - 128;
+      v = (n < NO) ? t.p[22][n] : 0.f;
+    }
+  }
+  out[idx] = v;
+}
+
 __global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {
   using P = CoarsePack;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,14 +236,22 @@ extern "C" int ens_pack_decoder(int level, const float *const *tensors_host, int
   PtrTable t;
   for (int i = 0; i < 24; ++i) t.p[i] = (i < n_tensors) ? tensors_host[i] : nullptr;
   for (int i = 0; i < n_tensors; ++i) if (!t.p[i]) return ENS_EINVAL;
-  const int total = packed_floats(level);
-  const int nb = (total + 255) / 256;
   cudaStream_t s = (cudaStream_t)stream;
+  auto nb = [](int total) { return (total + 255) / 256; };
   switch (level) {
-    case ENS_LEVEL_COARSE: pack_coarse_kernel<<<nb, 256, 0, s>>>(t, packed); break;
-    case ENS_LEVEL_MIDDLE: pack_mlp_kernel<32, 1><<<nb, 256, 0, s>>>(t, packed); break;
-    case ENS_LEVEL_FINE: pack_mlp_kernel<64, 1><<<nb, 256, 0, s>>>(t, packed); break;
-    default: pack_mlp_kernel<32, 4><<<nb, 256, 0, s>>>(t, packed); break;
+    case ENS_LEVEL_COARSE: pack_coarse_kernel<<<nb(CoarsePack::total()), 256, 0, s>>>(t, packed); break;
+    case ENS_LEVEL_MIDDLE:
+      pack_mlp_kernel<32, 1><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
+      pack_mlp_v2_kernel<32, 1><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
+      break;
+    case ENS_LEVEL_FINE:
+      pack_mlp_kernel<64, 1><<<nb(MlpPack<64>::total()), 256, 0, s>>>(t, packed);
+      pack_mlp_v2_kernel<64, 1><<<nb(MlpPackV2<64>::total()), 256, 0, s>>>(t, packed + MlpPack<64>::total());
+      break;
+    default:
+      pack_mlp_kernel<32, 4><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
+      pack_mlp_v2_kernel<32, 4><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
+      break;
   }
   ENS_CHECK_CUDA();
   return ENS_OK;

@@ -34,7 +34,7 @@ def test_library_loads_and_reports_version():
     from evennicer_slam_b200 import _lib
     L = _lib.lib()
     assert L.ens_version() == 1
-    assert L.ens_packed_decoder_floats(2) == 21028 and L.ens_decoder_grad_floats(3) == 15899
+    assert L.ens_packed_decoder_floats(2) == 21028 + 22244 and L.ens_decoder_grad_floats(3) == 15899
 
 
 def test_grid_layout_roundtrip():
@@ -379,7 +379,7 @@ def test_graphed_mapping_step_equals_eager(tiny):
         for p in decoders.parameters():
             p.grad = None
 
-    zero(); l0 = step(); torch.cuda.synchronize(); ref = grads()
+    zero(); l0 = float(step()); torch.cuda.synchronize(); ref = grads()   # float(): do not keep the autograd graph alive
     zero()
     gs = GraphedStep(step, warmup=2, device=DEV)
     for _ in range(2):
@@ -389,7 +389,7 @@ def test_graphed_mapping_step_equals_eager(tiny):
         l1 = gs()
     torch.cuda.synchronize()
     got = grads()
-    assert abs(float(l0) - float(l1)) < 1e-6 * abs(float(l0))
+    assert abs(l0 - float(l1)) < 1e-6 * abs(l0)
     assert len(got) == len(ref)
     for a, b in zip(got, ref):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
