@@ -81,6 +81,29 @@ struct MlpPackV2 {
 };
 __host__ __device__ constexpr int swz(int row, int k) { return k ^ ((row & 3) << 3); }
 
+// ---------------------------------------------------------------------------------------------
+// Packed decoder blob, "mma backward" layout: the TRANSPOSED matrices the data-gradient GEMMs read
+// (g_x = g_u W), each stored [in][out=32] with the same XOR swizzle, so their B fragments are again one
+// conflict-free 8-byte shared load per lane.
+//   B      [3][96]
+//   Wo     [4][32]
+//   W0T    [96][32]   W0T[k][n]  = pts_linears.0.weight[n][k]       (rows k >= 93 zero)
+//   W3eT   [96][32]   W3eT[k][n] = pts_linears.3.weight[n][k], k < 93
+//   block i=0..4:  WhT_i [32][32]  WhT[k][n] = hidden part of pts_linears.i.weight[n][k]  (i = 0: zeros)
+//                  WcT_i [32][32]  WcT[c][n] = fc_c.i.weight[n][c], c < 32   (only the first 32 feature
+//                                  channels carry gradient: the fine decoder's middle half is no_grad)
+// ---------------------------------------------------------------------------------------------
+struct MlpPackV2B {
+  __host__ __device__ static constexpr int off_B() { return 0; }
+  __host__ __device__ static constexpr int off_Wo() { return 3 * EMBP; }
+  __host__ __device__ static constexpr int off_W0T() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int off_W3eT() { return off_W0T() + EMBP * 32; }
+  __host__ __device__ static constexpr int off_L(int i) { return off_W3eT() + EMBP * 32 + i * 2048; }
+  __host__ __device__ static constexpr int in_WhT() { return 0; }
+  __host__ __device__ static constexpr int in_WcT() { return 1024; }
+  __host__ __device__ static constexpr int total() { return off_L(5); }
+};
+
 struct CoarsePack {
   __host__ __device__ static constexpr int K(int i) { return i == 3 ? 64 : 32; }
   __host__ __device__ static constexpr int off_W(int i) {
@@ -129,14 +152,16 @@ struct CoarseGrad {
   __host__ __device__ static constexpr int total() { return off_bo() + 1; }
 };
 
-// A packed blob holds the fma layout followed by the mma layout (coarse: fma only).
+// A packed blob holds the fma layout, the mma forward layout and the mma backward layout (coarse: fma only).
 __host__ __device__ inline int packed_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarsePack::total();
-    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total();
-    default: return MlpPack<32>::total() + MlpPackV2<32>::total();
+    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total() + MlpPackV2B::total();
+    default: return MlpPack<32>::total() + MlpPackV2<32>::total() + MlpPackV2B::total();
   }
 }
+template <int CD> __host__ __device__ constexpr int off_v2() { return MlpPack<CD>::total(); }
+template <int CD> __host__ __device__ constexpr int off_v2b() { return MlpPack<CD>::total() + MlpPackV2<CD>::total(); }
 __host__ __device__ inline int grad_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarseGrad::total();

@@ -203,6 +203,18 @@ struct FwdArgs {
   float *w_out, *raw_out;
 };
 
+struct BwdArgs {
+  DevScene sc;
+  RayArgs ra;
+  const float *raw;
+  const double *g_depth, *g_var;
+  const float *g_color;
+  float *ggrid[4];
+  float *gdec[4];
+  float *g_rays_o, *g_rays_d;
+  float *hscratch;          // activation scratch when decoder grads are requested (ens_bwd_workspace_bytes)
+};
+
 constexpr int NT_RENDER = 192;   // fma variant: 4 rays x 48 samples (6 x 32-sample rays)
 constexpr int NT_MMA = 384;      // mma variant: 12 warps x 32 points = 8 rays x 48 samples
 
@@ -244,5 +256,7 @@ inline void fill_ray_args(RayArgs &ra, const EnsRenderCfg *cfg, int stage, const
 int mma_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
                     float *out4, cudaStream_t s);
 int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s);
+int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s);
+int64_t mma_bwd_workspace_bytes(int64_t n_rays, int S);
 
 }  // namespace ens

@@ -137,6 +137,42 @@ __global__ void pack_mlp_v2_kernel(PtrTable t, float *__restrict__ out) {
   out[idx] = v;
 }
 
+// mma backward layout (see MlpPackV2B): transposed matrices, [in][32], XOR-swizzled columns
+template <int CD, int NO>
+__global__ void pack_mlp_v2b_kernel(PtrTable t, float *__restrict__ out) {
+  using P = MlpPackV2B;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P::total()) return;
+  float v = 0.f;
+  if (idx < P::off_Wo()) {
+    int r = idx / EMBP, k = idx % EMBP;
+    v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f;
+  } else if (idx < P::off_W0T()) {
+    int o = idx - P::off_Wo();
+    int n = o / 32, j = o % 32;
+    v = (n < NO) ? t.p[21][n * 32 + j] : 0.f;
+  } else if (idx < P::off_L(0)) {
+    const bool is3 = idx >= P::off_W3eT();
+    int o = idx - (is3 ? P::off_W3eT() : P::off_W0T());
+    int k = o / 32, n = swz(k, o % 32);               // row k (input feature), logical column n (output)
+    if (k < EMB) v = is3 ? t.p[11 + 2 * 3][n * 125 + k] : t.p[11][n * EMB + k];
+  } else {
+    int o = idx - P::off_L(0);
+    const int i = o / 2048;
+    o -= i * 2048;
+    if (o < 1024) {
+      int k = o / 32, n = swz(k, o % 32);
+      if (i == 3) v = t.p[11 + 2 * 3][n * 125 + EMB + k];
+      else if (i > 0) v = t.p[11 + 2 * i][n * 32 + k];
+    } else {
+      o -= 1024;
+      int c = o / 32, n = swz(c, o % 32);
+      v = t.p[2 * i][n * CD + c];
+    }
+  }
+  out[idx] = v;
+}
+
 __global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {
   using P = CoarsePack;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,14 +279,17 @@ extern "C" int ens_pack_decoder(int level, const float *const *tensors_host, int
     case ENS_LEVEL_MIDDLE:
       pack_mlp_kernel<32, 1><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
       pack_mlp_v2_kernel<32, 1><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
+      pack_mlp_v2b_kernel<32, 1><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<32>());
       break;
     case ENS_LEVEL_FINE:
       pack_mlp_kernel<64, 1><<<nb(MlpPack<64>::total()), 256, 0, s>>>(t, packed);
       pack_mlp_v2_kernel<64, 1><<<nb(MlpPackV2<64>::total()), 256, 0, s>>>(t, packed + MlpPack<64>::total());
+      pack_mlp_v2b_kernel<64, 1><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<64>());
       break;
     default:
       pack_mlp_kernel<32, 4><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
       pack_mlp_v2_kernel<32, 4><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
+      pack_mlp_v2b_kernel<32, 4><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<32>());
       break;
   }
   ENS_CHECK_CUDA();

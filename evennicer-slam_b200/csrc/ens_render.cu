@@ -644,17 +644,6 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(FwdArgs a) {
 // =============================================================================================
 // render backward
 // =============================================================================================
-struct BwdArgs {
-  DevScene sc;
-  RayArgs ra;
-  const float *raw;
-  const double *g_depth, *g_var;
-  const float *g_color;
-  float *ggrid[4];
-  float *gdec[4];
-  float *g_rays_o, *g_rays_d;
-  float *hscratch;          // [R*S][160] floats when decoder grads are requested
-};
 
 // one decoder's backward for this thread's point; CTA-collective when WG.
 template <int NT, int LEVEL, int CD, int NO, bool WG>
@@ -952,9 +941,16 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   }
 }
 
+static bool use_mma_backward() {
+  const char *v = std::getenv("ENS_BWD_VARIANT");
+  return !(v && std::strcmp(v, "fma") == 0);
+}
+
 extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads) {
   if (!want_decoder_grads || n_rays <= 0 || n_samples_total <= 0) return 0;
-  return (n_rays * (int64_t)n_samples_total + 1) * 160 * (int64_t)sizeof(float);   // +1: dump row for idle lanes
+  const int64_t fma = (n_rays * (int64_t)n_samples_total + 1) * 160 * (int64_t)sizeof(float);   // +1: dump row for idle lanes
+  const int64_t mma = mma_bwd_workspace_bytes(n_rays, n_samples_total);
+  return fma > mma ? fma : mma;
 }
 
 extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
@@ -993,6 +989,10 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
     if (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1)) return ENS_ESHAPE;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_mma_backward()) {
+    rc = mma_render_bwd(a, stage, wg, s);
+    if (rc != ENS_EUNSUPPORTED) return rc;       // coarse stage: fma kernels below
+  }
 #define ENS_BWD_CASE(ST) \
   case ST: return wg ? launch_bwd<ST, true>(a, s) : launch_bwd<ST, false>(a, s);
   switch (stage) {

@@ -1,0 +1,739 @@
+// Fused render BACKWARD on the tensor pipe (variant "mma"): recompute + data gradients + weight gradients
+// of Renderer.render_batch_ray, stages middle / fine / color.
+//
+// Mapping (same as the forward, ens_render_mma.cu): a CTA owns whole rays; thread tid = sample point
+// (ray tid / S, sample tid % S); a warp's 32 points are two m16 row tiles; lane (g = L/4, t = L%4) holds
+// rows {g, g+8, g+16, g+24} x columns {8n+2t, 8n+2t+1} of every 32x32 activation / gradient tile.
+//
+// Per decoder:
+//   1. forward recompute (3xTF32 mma.sync, activations chained in registers); keeps the five relu masks
+//      (one bit per accumulator element) and, when decoder gradients are wanted, spills h_0..h_3 as
+//      swizzled 32x32 tiles to an L2-resident scratch (they are the x operands of the weight-gradient GEMMs);
+//   2. data gradients  g_x = g_u W  with the TRANSPOSED weight blob (MlpPackV2B): the gradient tile in
+//      accumulator layout is again directly the A fragment of the next GEMM;  g_c += g_h Wc  accumulates the
+//      feature gradient over the five blocks;
+//   3. weight gradients  dW = sum_pt g_u^T x  are GEMMs over the POINT dimension.  Both operands are
+//      accumulator-layout tiles with points on the fragment rows, so they are staged through shared memory
+//      (swizzled, conflict-free both ways) and the CTA's warps split (row tile, third of the points) items
+//      of the output; results leave with RED.ADD to the flat per-decoder gradient buffer;
+//   4. trilinear backward: the feature gradient is transposed through the warp's own feature tile so that 8
+//      lanes own one point's 128-byte voxel line: red.global.add.v4.f32 per corner, and the coordinate
+//      gradient from the re-read corner values;
+//   5. Fourier embedding backward in three 32-column chunks (sincos recomputed in accumulator layout).
+//
+// Two instantiations per stage: WG = decoder gradients on (mapping: 192 threads = 4 rays, three staging
+// tiles) and WG = off (tracking / event render: 256 threads = 5 rays, no staging, no CTA barriers in the
+// layer loop).
+#include "ens_mma.cuh"
+
+namespace ens {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers on accumulator-layout tiles
+// ---------------------------------------------------------------------------------------------
+#define ENS_FOR_TILE(m, nt, e)            \
+  _Pragma("unroll") for (int m = 0; m < 2; ++m) \
+  _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) \
+  _Pragma("unroll") for (int e = 0; e < 4; ++e)
+
+__device__ __forceinline__ void zero_tile(float (&a)[2][4][4]) {
+  ENS_FOR_TILE(m, nt, e) a[m][nt][e] = 0.f;
+}
+
+// acc = relu(acc) + bc ; returns the mask of acc > 0 (bit (m*4+nt)*4+e)
+__device__ __forceinline__ uint32_t relu_add_bias_mask(float (&acc)[2][4][4], const float *__restrict__ bc, int t) {
+  uint32_t mk = 0;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 v = *reinterpret_cast<const float2 *>(bc + 8 * nt + 2 * t);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = acc[m][nt][e];
+        if (a > 0.f) mk |= 1u << ((m * 4 + nt) * 4 + e);
+        acc[m][nt][e] = fmaxf(a, 0.f) + ((e & 1) ? v.y : v.x);
+      }
+    }
+  }
+  return mk;
+}
+
+// store an accumulator-layout tile as a swizzled [32][LD] row-major tile (shared or global):
+// element (row r, col c) at base + r*LD + ((c0 + c) ^ ((r & 3) << 3))
+template <int LD>
+__device__ __forceinline__ void store_tile(float *__restrict__ base, int c0, const float (&x)[2][4][4], int g, int t) {
+  const int sw = (g & 3) << 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = (c0 + 8 * nt + 2 * t) ^ sw;
+      *reinterpret_cast<float2 *>(base + (16 * m + g) * LD + col) = make_float2(x[m][nt][0], x[m][nt][1]);
+      *reinterpret_cast<float2 *>(base + (16 * m + g + 8) * LD + col) = make_float2(x[m][nt][2], x[m][nt][3]);
+    }
+  }
+}
+
+// asynchronous 4 KB tile copy global -> shared by one warp (no registers)
+__device__ __forceinline__ void cp_async_tile(float *__restrict__ sdst, const float *__restrict__ gsrc, int lane) {
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(sdst);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int idx = (q * 32 + lane) * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + idx * 4), "l"(gsrc + idx) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient GEMM item:  d[nt](n, k) += sum_{pt in [p0,p1)} A[pt][16m + n] * B[pt][bcol0 + 8nt + k]
+// A: swizzled [pts][LDA] tile (columns a0 ..), B: swizzled [pts][LDB] tile.  3xTF32.
+// bsum[0..1] accumulate the column sums of A (rows 16m+g, 16m+g+8 of the output) = bias gradients.
+// ---------------------------------------------------------------------------------------------
+template <int LDA, int LDB, int NTILES>
+__device__ __forceinline__ void wgrad_mma(float (&d)[NTILES][4], float (&bsum)[2], const float *__restrict__ A,
+                                          int acol0, int m, const float *__restrict__ B, int bcol0, int p0, int p1,
+                                          int g, int t) {
+  const int sw = t << 3;                      // ((pt0 + t) & 3) << 3 for pt0 % 8 == 0; rows t and t+4 agree
+  const int ac0 = (acol0 + 16 * m + g) ^ sw, ac1 = (acol0 + 16 * m + g + 8) ^ sw;
+#pragma unroll 2
+  for (int pt0 = p0; pt0 < p1; pt0 += 8) {
+    const float *ar0 = A + (pt0 + t) * LDA, *ar1 = ar0 + 4 * LDA;
+    const float a0 = ar0[ac0], a1 = ar0[ac1], a2 = ar1[ac0], a3 = ar1[ac1];
+    bsum[0] += a0 + a2;
+    bsum[1] += a1 + a3;
+    uint32_t ah[4], al[4];
+    split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+    split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+    const float *br0 = B + (pt0 + t) * LDB, *br1 = br0 + 4 * LDB;
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) {
+      const int bc = (bcol0 + 8 * nt + g) ^ sw;
+      uint32_t bh0, bl0, bh1, bl1;
+      split_tf32(br0[bc], bh0, bl0);
+      split_tf32(br1[bc], bh1, bl1);
+      mma_tf32(d[nt], al, bh0, bh1);
+      mma_tf32(d[nt], ah, bl0, bl1);
+      mma_tf32(d[nt], ah, bh0, bh1);
+    }
+  }
+}
+
+// emit a [16 x 8*NTILES] output strip: out[(16m + n) * ldw + kofs + k] += d, k < klim
+template <int NTILES>
+__device__ __forceinline__ void emit_strip(float *__restrict__ out, int ldw, int kofs, int klim, int m,
+                                           const float (&d)[NTILES][4], int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < NTILES; ++nt) {
+    const int k = 8 * nt + 2 * t;
+    float *r0 = out + (16 * m + g) * ldw + kofs, *r1 = r0 + 8 * ldw;
+    if (k < klim) { atomicAdd(r0 + k, d[nt][0]); atomicAdd(r1 + k, d[nt][2]); }
+    if (k + 1 < klim) { atomicAdd(r0 + k + 1, d[nt][1]); atomicAdd(r1 + k + 1, d[nt][3]); }
+  }
+}
+// bias: column sums held per lane for rows 16m+g and 16m+g+8, partial over t
+__device__ __forceinline__ void emit_bias(float *__restrict__ out, int m, float (&bsum)[2], int g, int t) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v = bsum[h];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) atomicAdd(out + 16 * m + g + 8 * h, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trilinear backward for the warp's 32 points.  crow: the warp's feature-tile rows; columns 0..31 hold the
+// feature gradient g_c (swizzled) -- written by store_tile just before.  8 lanes per point.
+//   ggrid != null : scatter  w_corner * g_c  into the native-layout gradient grid (valid points only)
+//   want_coord    : gpn = d L / d (normalised coords) of the owner lane's point
+// ---------------------------------------------------------------------------------------------
+template <int RS>
+__device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, float *__restrict__ ggrid,
+                                                const int dims[3], const Vox &v, bool valid,
+                                                const float *__restrict__ crow, bool want_coord, float (&gpn)[3]) {
+  const int lane = threadIdx.x & 31;
+  const int X = dims[2], Y = dims[1], Z = dims[0];
+  const int base = ((v.z0 * Y + v.y0) * X + v.x0) * C;
+  const bool okx = v.x0 + 1 < X, oky = v.y0 + 1 < Y, okz = v.z0 + 1 < Z;
+  const unsigned okbits = (unsigned)okx | ((unsigned)oky << 1) | ((unsigned)okz << 2) | ((unsigned)valid << 3);
+  const int cq = lane & 7, pp = lane >> 3;
+  const int sx = C, sy = X * C, sz = X * Y * C;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll 1
+  for (int grp = 0; grp < 8; ++grp) {
+    const int src = 4 * grp + pp;
+    const int b = __shfl_sync(0xffffffffu, base, src);
+    const float fx1 = __shfl_sync(0xffffffffu, v.fx, src), fx0 = __shfl_sync(0xffffffffu, v.gx, src);
+    const float fy1 = __shfl_sync(0xffffffffu, v.fy, src), fy0 = __shfl_sync(0xffffffffu, v.gy, src);
+    const float fz1 = __shfl_sync(0xffffffffu, v.fz, src), fz0 = __shfl_sync(0xffffffffu, v.gz, src);
+    const unsigned okb = __shfl_sync(0xffffffffu, okbits, src);
+    const int ox = (okb & 1u) ? sx : 0, oy = (okb & 2u) ? sy : 0, oz = (okb & 4u) ? sz : 0;
+    const float4 gc = *reinterpret_cast<const float4 *>(crow + src * RS + ((4 * cq) ^ ((src & 3) << 3)));
+    const int off0 = b + 4 * cq;
+    float gix = 0.f, giy = 0.f, giz = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool inr = (!(c & 1) || (okb & 1u)) && (!(c & 2) || (okb & 2u)) && (!(c & 4) || (okb & 4u));
+      const int off = off0 + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0);
+      const float wx = (c & 1) ? fx1 : fx0, wy = (c & 2) ? fy1 : fy0, wz = (c & 4) ? fz1 : fz0;
+      if (inr) {
+        if (ggrid != nullptr && (okb & 8u)) {
+          const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+          if (w != 0.f) red_add_v4(ggrid + off, w * gc.x, w * gc.y, w * gc.z, w * gc.w);
+        }
+        if (want_coord) {
+          const float4 a = __ldg(reinterpret_cast<const float4 *>(grid + off));
+          const float dot = fmaf(a.w, gc.w, fmaf(a.z, gc.z, fmaf(a.y, gc.y, a.x * gc.x)));
+          gix += ((c & 1) ? 1.f : -1.f) * wy * wz * dot;
+          giy += ((c & 2) ? 1.f : -1.f) * wx * wz * dot;
+          giz += ((c & 4) ? 1.f : -1.f) * wx * wy * dot;
+        }
+      }
+    }
+    if (want_coord) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, o);
+        giy += __shfl_xor_sync(0xffffffffu, giy, o);
+        giz += __shfl_xor_sync(0xffffffffu, giz, o);
+      }
+      // point 4*grp + pp was handled by lanes 8pp..8pp+7: deliver to its owner lane
+      const float ax = __shfl_sync(0xffffffffu, gix, 8 * (lane & 3));
+      const float ay = __shfl_sync(0xffffffffu, giy, 8 * (lane & 3));
+      const float az = __shfl_sync(0xffffffffu, giz, 8 * (lane & 3));
+      if ((lane >> 2) == grp) { mx = ax; my = ay; mz = az; }
+    }
+  }
+  gpn[0] = mx * v.sx; gpn[1] = my * v.sy; gpn[2] = mz * v.sz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel configuration
+// ---------------------------------------------------------------------------------------------
+template <int STAGE, bool WG>
+struct BwdCfg {
+  static constexpr int NT = WG ? 192 : 256;
+  static constexpr int NW = NT / 32;
+  static constexpr int RS = MmaStage<STAGE>::RS;
+  static constexpr int WREG = MmaStage<STAGE>::WMAX;                    // >= MlpPackV2B::total()
+  static constexpr int TILE = NT * 32;                                  // floats of one staging tile
+  static constexpr int NTILES = WG ? 3 : 0;                             // sG, sG2, sX
+  static constexpr int MISC_BYTES = NT * 56;                            // placement / compositing scratch, later sgp
+  static constexpr size_t smem_bytes() {
+    return (size_t)(WREG + NT * RS + NTILES * TILE + (WG ? NT * 4 : 0)) * 4 + MISC_BYTES;
+  }
+};
+static_assert(MlpPackV2B::total() <= MlpPackV2<32>::total(), "backward blob must fit the forward weight region");
+
+template <int CD, int NO>
+__device__ __forceinline__ int grad_off_W(int i) {      // runtime-i MlpGrad<CD,NO>::off_W
+  return MlpGrad<CD, NO>::off_W(0) + (i >= 1 ? 32 * 93 + 32 : 0) + (i >= 2 ? 1056 : 0) + (i >= 3 ? 1056 : 0) +
+         (i >= 4 ? 32 * 125 + 32 : 0);
+}
+
+struct WarpCtx {
+  int lane, g, t, warp;
+  float *crow;       // warp's feature-tile rows
+  float *sG, *sG2, *sX;   // CTA tiles (WG)
+  float *sP;         // [NT][4] points (WG)
+  float *hs;         // global scratch of this warp: 4 tiles of 1024 floats (WG)
+};
+
+// ---------------------------------------------------------------------------------------------
+// one decoder: recompute + backward for the warp's 32 points.  CTA-collective.
+//   gout[NO]   : d L / d (decoder outputs) of the OWNER lane's point
+//   p32        : owner lane's p.float();  pn: its normalised coordinates
+//   gp         : owner lane's accumulated d L / d p (float64)
+// ---------------------------------------------------------------------------------------------
+template <int STAGE, bool WG, int LEVEL, int CD, int NO>
+__device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restrict__ sw, const WarpCtx &w,
+                                                const float pn[3], const float p32[3], const float (&gout)[NO],
+                                                bool valid, bool want_rays, double gp[3]) {
+  using CFG = BwdCfg<STAGE, WG>;
+  constexpr int RS = CFG::RS;
+  constexpr int NT = CFG::NT;
+  using PF = MlpPackV2<CD>;
+  using PB = MlpPackV2B;
+  using GO = MlpGrad<CD, NO>;
+  constexpr int C0 = (LEVEL == ENS_LEVEL_MIDDLE && RS == 64) ? 32 : 0;   // where this decoder's own features live
+  const int lane = w.lane, g = w.g, t = w.t;
+  float *gdec = a.gdec[LEVEL];
+  float *ggrid = a.ggrid[LEVEL];
+  const bool need_emb = WG || want_rays;
+
+  // ---- 1. stage the forward blob, gather features ----
+  __syncthreads();
+  stage_blob(sw, a.sc.w[LEVEL] + off_v2<CD>(), PF::total());
+  const Vox v = make_vox(pn, a.sc.dims[LEVEL]);
+  gather_warp<RS>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], v, w.crow, C0);
+  __syncthreads();
+
+  float rx[4], ry[4], rz[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rx[j] = __shfl_sync(0xffffffffu, p32[0], g + 8 * j);
+    ry[j] = __shfl_sync(0xffffffffu, p32[1], g + 8 * j);
+    rz[j] = __shfl_sync(0xffffffffu, p32[2], g + 8 * j);
+  }
+
+  // ---- 2. forward recompute ----
+  uint32_t mask[5];
+  float gh[2][4][4];
+  {
+    float acc[2][4][4], acc3[2][4][4];
+    set_bias(acc, sw + PF::off_L(0) + PF::in_b(), t);
+    set_bias(acc3, sw + PF::off_L(3) + PF::in_b(), t);
+#pragma unroll 1
+    for (int kt = 0; kt < EMBP / 8; ++kt) {
+      const float *B = sw + PF::off_B() + 8 * kt + 2 * t;
+      const float2 b0 = *reinterpret_cast<const float2 *>(B);
+      const float2 b1 = *reinterpret_cast<const float2 *>(B + EMBP);
+      const float2 b2 = *reinterpret_cast<const float2 *>(B + 2 * EMBP);
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * m + h;
+          const float q0 = fmaf(rz[j], b2.x, fmaf(ry[j], b1.x, rx[j] * b0.x));
+          const float q1 = fmaf(rz[j], b2.y, fmaf(ry[j], b1.y, rx[j] * b0.y));
+          split_tf32(fast_sin(q0), ah[m][h], al[m][h]);
+          split_tf32(fast_sin(q1), ah[m][2 + h], al[m][2 + h]);
+        }
+      }
+      mma_ktile<EMBP>(acc, ah, al, sw + PF::off_W0(), kt, g, t);
+      mma_ktile<EMBP>(acc3, ah, al, sw + PF::off_W3e(), kt, g, t);
+    }
+    float x[2][4][4];
+#pragma unroll 1
+    for (int i = 0; i < 5; ++i) {
+      const float *L = sw + PF::off_L(0) + i * PF::block_floats();
+      if (i > 0) {
+        ENS_FOR_TILE(m, nt, e) {
+          x[m][nt][e] = acc[m][nt][e];
+          acc[m][nt][e] = acc3[m][nt][e];
+        }
+        if (i != 3) set_bias(acc, L + PF::in_b(), t);
+        gemm_hidden(acc, x, L + PF::in_Wh(), g, t);
+      }
+      const uint32_t mk = relu_add_bias_mask(acc, L + PF::in_bc(), t);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) if (k == i) mask[k] = mk;
+      gemm_features<CD, RS>(acc, w.crow, C0 == 32 ? 32 : 0, L + PF::in_Wc(), g, t);
+      if (WG && i < 4) store_tile<32>(w.hs + i * 1024, 0, acc, g, t);      // h_i = x_{i+1}
+    }
+    // decoder-output gradients of my four rows
+    float gr[4][NO];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) gr[j][o] = __shfl_sync(0xffffffffu, gout[o], g + 8 * j);
+    if (WG) {
+      // dWo[o][n] = sum_pt gout[pt][o] h4[pt][n]; dbo[o] = sum_pt gout[pt][o]
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float s = gr[0][o] * acc[0][nt][c];
+            s = fmaf(gr[1][o], acc[0][nt][2 + c], s);
+            s = fmaf(gr[2][o], acc[1][nt][c], s);
+            s = fmaf(gr[3][o], acc[1][nt][2 + c], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            if (g == 0) atomicAdd(gdec + GO::off_Wo() + o * 32 + 8 * nt + 2 * t + c, s);
+          }
+        }
+        float sb = gout[o];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        if (lane == 0) atomicAdd(gdec + GO::off_bo() + o, sb);
+      }
+    }
+    // g_h4 = Wo^T gout
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float2 wo[NO];
+#pragma unroll
+      for (int o = 0; o < NO; ++o) wo[o] = *reinterpret_cast<const float2 *>(sw + PF::off_Wo() + o * 32 + 8 * nt + 2 * t);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 2 * m + (e >> 1);
+          float s = 0.f;
+#pragma unroll
+          for (int o = 0; o < NO; ++o) s = fmaf(gr[j][o], (e & 1) ? wo[o].y : wo[o].x, s);
+          gh[m][nt][e] = s;
+        }
+      }
+    }
+  }
+
+  // ---- 3. stage the backward (transposed) blob ----
+  __syncthreads();
+  stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
+  if (WG) cp_async_tile(w.sX, w.hs + 3 * 1024, lane);                     // x_4 = h_3
+  __syncthreads();
+
+  // ---- 4. blocks 4..0 ----
+  float gc[2][4][4], gu[2][4][4], gu3[2][4][4];
+  zero_tile(gc);
+#pragma unroll 1
+  for (int i = 4; i >= 0; --i) {
+    const float *L = sw + PB::off_L(0) + i * 2048;
+    uint32_t mk = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) if (k == i) mk = mask[k];
+    ENS_FOR_TILE(m, nt, e) gu[m][nt][e] = ((mk >> ((m * 4 + nt) * 4 + e)) & 1u) ? gh[m][nt][e] : 0.f;
+    if (WG) {
+      store_tile<32>(w.sG, 0, gh, g, t);
+      store_tile<32>(w.sG2, 0, gu, g, t);
+    }
+    if (i == 3) { ENS_FOR_TILE(m, nt, e) gu3[m][nt][e] = gu[m][nt][e]; }
+    gemm_hidden(gc, gh, L + PB::in_WcT(), g, t);                          // g_c += g_h Wc[:, :32]
+    if (i > 0) {
+      zero_tile(gh);
+      gemm_hidden(gh, gu, L + PB::in_WhT(), g, t);                        // g_h_{i-1} = g_u W_i (hidden part)
+    }
+    if (WG) {
+      cp_async_wait_all();
+      __syncthreads();
+      // items: round r = B source (0: x tile -> dW_i ; 1: own features -> dWc_i[:, :32] ; 2: concat half);
+      // warp -> (row tile m = warp / 3, third of the points warp % 3)
+      const int m = w.warp / 3, p0 = (w.warp % 3) * (NT / 3), p1 = p0 + NT / 3;
+      const float *feat = w.crow - w.warp * 32 * RS;                      // CTA feature tile
+      const float *G = w.sG - w.warp * 1024, *G2 = w.sG2 - w.warp * 1024, *Xt = w.sX - w.warp * 1024;
+      if (i > 0) {
+        float d[4][4] = {}, bs[2] = {0.f, 0.f};
+        wgrad_mma<32, 32, 4>(d, bs, G2, 0, m, Xt, 0, p0, p1, g, t);
+        const int K = (i == 3) ? 125 : 32;
+        float *out = gdec + grad_off_W<CD, NO>(i);
+        emit_strip<4>(out, K, (i == 3) ? EMB : 0, 32, m, d, g, t);
+        emit_bias(out + 32 * K, m, bs, g, t);
+      }
+      {
+        float d[4][4] = {}, bs[2] = {0.f, 0.f};
+        wgrad_mma<32, RS, 4>(d, bs, G, 0, m, feat, C0, p0, p1, g, t);
+        float *out = gdec + GO::off_Wc(0) + i * (32 * CD + 32);
+        emit_strip<4>(out, CD, 0, 32, m, d, g, t);
+        emit_bias(out + 32 * CD, m, bs, g, t);
+      }
+      if (CD == 64) {
+        float d[4][4] = {}, bs[2] = {0.f, 0.f};
+        wgrad_mma<32, RS, 4>(d, bs, G, 0, m, feat, 32, p0, p1, g, t);
+        float *out = gdec + GO::off_Wc(0) + i * (32 * CD + 32);
+        emit_strip<4>(out, CD, 32, 32, m, d, g, t);
+      }
+      __syncthreads();
+      if (i >= 2) cp_async_tile(w.sX, w.hs + (i - 2) * 1024, lane);       // x_{i-1} = h_{i-2}
+    }
+  }
+  // gu = g_u0 (registers; WG: also in sG2), gu3 = g_u3.
+
+  // ---- 5. trilinear backward ----
+  if (ggrid != nullptr || want_rays) {
+    __syncwarp();
+    store_tile<RS>(w.crow, 0, gc, g, t);
+    __syncwarp();
+    float gpn[3];
+    gather_bwd_warp<RS>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], v, valid, w.crow, want_rays, gpn);
+    if (want_rays) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        gp[k] += __ddiv_rn((double)gpn[k] * 2.0, __dsub_rn(a.sc.hi[k], a.sc.lo[k]));
+    }
+    __syncwarp();
+  }
+
+  // ---- 6. Fourier embedding backward, three 32-column chunks ----
+  if (need_emb) {
+    if (WG) store_tile<32>(w.sG, 0, gu3, g, t);
+    float gpp[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gpp[j][0] = gpp[j][1] = gpp[j][2] = 0.f;
+#pragma unroll 1
+    for (int jc = 0; jc < 3; ++jc) {
+      float acc[2][4][4];
+      zero_tile(acc);
+      gemm_hidden(acc, gu, sw + PB::off_W0T() + jc * 1024, g, t);
+      gemm_hidden(acc, gu3, sw + PB::off_W3eT() + jc * 1024, g, t);
+      float ev[2][4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float *B = sw + PB::off_B() + 32 * jc + 8 * nt + 2 * t;
+        const float2 b0 = *reinterpret_cast<const float2 *>(B);
+        const float2 b1 = *reinterpret_cast<const float2 *>(B + EMBP);
+        const float2 b2 = *reinterpret_cast<const float2 *>(B + 2 * EMBP);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 2 * m + (e >> 1);
+            const float bx = (e & 1) ? b0.y : b0.x, by = (e & 1) ? b1.y : b1.x, bz = (e & 1) ? b2.y : b2.x;
+            const float q = fmaf(rz[j], bz, fmaf(ry[j], by, rx[j] * bx));
+            float sq, cq;
+            fast_sincos(q, sq, cq);
+            const float gq = acc[m][nt][e] * cq;
+            acc[m][nt][e] = gq;
+            ev[m][nt][e] = sq;
+            gpp[j][0] = fmaf(bx, gq, gpp[j][0]);
+            gpp[j][1] = fmaf(by, gq, gpp[j][1]);
+            gpp[j][2] = fmaf(bz, gq, gpp[j][2]);
+          }
+        }
+      }
+      if (WG) {
+        store_tile<32>(w.sX, 0, ev, g, t);
+        store_tile<RS>(w.crow, 0, acc, g, t);                              // g_q chunk (feature columns 0..31 are dead)
+        __syncthreads();
+        const int m = w.warp / 3, p0 = (w.warp % 3) * (NT / 3), p1 = p0 + NT / 3;
+        const float *feat = w.crow - w.warp * 32 * RS;
+        const float *G = w.sG - w.warp * 1024, *G2 = w.sG2 - w.warp * 1024, *Xt = w.sX - w.warp * 1024;
+        const int klim = EMB - 32 * jc;                                    // 93 real columns
+        {   // dW0[:, 32jc ..] = g_u0^T e ; db_0
+          float d[4][4] = {}, bs[2] = {0.f, 0.f};
+          wgrad_mma<32, 32, 4>(d, bs, G2, 0, m, Xt, 0, p0, p1, g, t);
+          float *out = gdec + GO::off_W(0);
+          emit_strip<4>(out, EMB, 32 * jc, klim, m, d, g, t);
+          if (jc == 0) emit_bias(out + 32 * EMB, m, bs, g, t);
+        }
+        {   // dW3[:, 32jc ..] (embedding half of the skip layer) = g_u3^T e
+          float d[4][4] = {}, bs[2] = {0.f, 0.f};
+          wgrad_mma<32, 32, 4>(d, bs, G, 0, m, Xt, 0, p0, p1, g, t);
+          emit_strip<4>(gdec + GO::off_W(3), 125, 32 * jc, klim, m, d, g, t);
+        }
+        {   // dB[r][32jc + k] = sum_pt p[pt][r] g_q[pt][k]:  rows = k, one 8-wide column tile = (x, y, z, 0, ...)
+          float d[1][4] = {}, bs[2] = {0.f, 0.f};
+          const int sw8 = t << 3;
+          const int ac0 = (16 * m + g) ^ sw8, ac1 = (16 * m + g + 8) ^ sw8;
+#pragma unroll 2
+          for (int pt0 = p0; pt0 < p1; pt0 += 8) {
+            const float *ar0 = feat + (pt0 + t) * RS, *ar1 = ar0 + 4 * RS;
+            uint32_t ah[4], al[4];
+            split_tf32(ar0[ac0], ah[0], al[0]); split_tf32(ar0[ac1], ah[1], al[1]);
+            split_tf32(ar1[ac0], ah[2], al[2]); split_tf32(ar1[ac1], ah[3], al[3]);
+            const float pb0 = (g < 4) ? w.sP[(pt0 + t) * 4 + g] : 0.f;
+            const float pb1 = (g < 4) ? w.sP[(pt0 + t + 4) * 4 + g] : 0.f;
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(pb0, bh0, bl0);
+            split_tf32(pb1, bh1, bl1);
+            mma_tf32(d[0], al, bh0, bh1);
+            mma_tf32(d[0], ah, bl0, bl1);
+            mma_tf32(d[0], ah, bh0, bh1);
+          }
+          (void)bs;
+          // d: (k = 16m+g (+8), r = 2t, 2t+1)
+          float *out = gdec + GO::off_B() + 32 * jc;
+          const int k0 = 16 * m + g, k1 = k0 + 8;
+          const int r = 2 * t;
+          if (r < 3) {
+            if (k0 < klim) atomicAdd(out + r * EMB + k0, d[0][0]);
+            if (k1 < klim) atomicAdd(out + r * EMB + k1, d[0][2]);
+          }
+          if (r + 1 < 3) {
+            if (k0 < klim) atomicAdd(out + (r + 1) * EMB + k0, d[0][1]);
+            if (k1 < klim) atomicAdd(out + (r + 1) * EMB + k1, d[0][3]);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (want_rays) {
+      // quad-reduce the per-row partials and hand row j of quad g to its owner lane g + 8j
+      float mine[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float s = gpp[j][k];
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          const float got = __shfl_sync(0xffffffffu, s, (lane & 7) * 4);
+          if ((lane >> 3) == j) mine[k] = got;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gp[k] += (double)mine[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int STAGE, bool WG>
+__global__ void __launch_bounds__(BwdCfg<STAGE, WG>::NT, 1) render_bwd_mma_kernel(BwdArgs a) {
+  using CFG = BwdCfg<STAGE, WG>;
+  constexpr int NT = CFG::NT;
+  constexpr int RS = CFG::RS;
+  extern __shared__ __align__(16) float smem[];
+  float *sw = smem;
+  float *sfeat = smem + CFG::WREG;
+  float *tiles = sfeat + NT * RS;
+  float *sP = tiles + CFG::NTILES * CFG::TILE;
+  char *misc = reinterpret_cast<char *>(sP + (WG ? NT * 4 : 0));
+  // misc region: placement / compositing scratch; later the per-point ray gradients
+  double *zc = reinterpret_cast<double *>(misc);
+  double *zs = zc + NT;
+  double *sgw = zs + NT;
+  float4 *sraw = reinterpret_cast<float4 *>(sgw + NT);
+  float *salpha = reinterpret_cast<float *>(sraw + NT);
+  float *sT = salpha + NT;
+  float *sw_ = sT + NT;
+  float *ssuf = sw_ + NT;
+  double *sgp = reinterpret_cast<double *>(misc);            // [NT][3] doubles = 24 B/pt, reuses the region at the end
+
+  const RayArgs &ra = a.ra;
+  const int S = ra.S;
+  const int rl = threadIdx.x / S, s = threadIdx.x % S;
+  const int64_t ray = (int64_t)blockIdx.x * ra.rpc + rl;
+  const bool valid = (rl < ra.rpc) && (ray < ra.R);
+  const int64_t pidx = valid ? ray * S + s : 0;
+  float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = ra.rays_o[ray * 3 + k]; d[k] = ra.rays_d[ray * 3 + k]; }
+  }
+  const double z = place_sample(ra, a.sc, valid, ray, rl, s, o, d, zc, zs);
+  double p[3];
+  float pn[3], p32[3];
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p[k] = __dadd_rn((double)o[k], __dmul_rn((double)d[k], z));
+    p32[k] = __double2float_rn(p[k]);
+    inside &= (p[k] < a.sc.hi[k]) && (p[k] > a.sc.lo[k]);
+  }
+  normalize64(p, a.sc.lo, a.sc.hi, pn);
+
+  // ---- compositing forward (from the saved raw) and backward ----
+  float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) raw = reinterpret_cast<const float4 *>(a.raw)[pidx];
+  const float alpha = 1.f / (1.f + expf(-(10.f * raw.w)));
+  __syncthreads();
+  zs[threadIdx.x] = z;
+  sraw[threadIdx.x] = raw;
+  salpha[threadIdx.x] = alpha;
+  __syncthreads();
+  if (valid && s == 0) {
+    float T = 1.f;
+    for (int k = 0; k < S; ++k) {
+      sT[threadIdx.x + k] = T;
+      sw_[threadIdx.x + k] = __fmul_rn(salpha[threadIdx.x + k], T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, salpha[threadIdx.x + k]), 1e-10f));
+    }
+    double dep = 0.0;
+    for (int k = 0; k < S; ++k) dep += (double)sw_[threadIdx.x + k] * zs[threadIdx.x + k];
+    double wdz = 0.0;
+    for (int k = 0; k < S; ++k) wdz += (double)sw_[threadIdx.x + k] * (zs[threadIdx.x + k] - dep);
+    const double gd = a.g_depth ? a.g_depth[ray] : 0.0;
+    const double gv = a.g_var ? a.g_var[ray] : 0.0;
+    const double gdt = gd + gv * (-2.0 * wdz);
+    float gcl[3] = {0.f, 0.f, 0.f};
+    if (a.g_color) { gcl[0] = a.g_color[ray * 3]; gcl[1] = a.g_color[ray * 3 + 1]; gcl[2] = a.g_color[ray * 3 + 2]; }
+    for (int k = 0; k < S; ++k) {
+      const float4 rk = sraw[threadIdx.x + k];
+      const double zk = zs[threadIdx.x + k], dz = zk - dep;
+      sgw[threadIdx.x + k] = (double)rk.x * gcl[0] + (double)rk.y * gcl[1] + (double)rk.z * gcl[2] + gdt * zk + gv * dz * dz;
+    }
+    float accs = 0.f;
+    for (int k = S - 1; k >= 0; --k) {
+      ssuf[threadIdx.x + k] = accs;
+      accs += sw_[threadIdx.x + k] * (float)sgw[threadIdx.x + k];
+    }
+  }
+  __syncthreads();
+  float g_occ = 0.f, g_rgb[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+    const float gw = (float)sgw[threadIdx.x];
+    const float om = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    const float g_alpha = sT[threadIdx.x] * gw - ssuf[threadIdx.x] / om;
+    g_occ = inside ? 10.f * alpha * (1.f - alpha) * g_alpha : 0.f;       // raw[~mask,3]=100 cuts the graph
+    const float wv = sw_[threadIdx.x];
+    if (a.g_color) {
+      g_rgb[0] = wv * a.g_color[ray * 3]; g_rgb[1] = wv * a.g_color[ray * 3 + 1]; g_rgb[2] = wv * a.g_color[ray * 3 + 2];
+    }
+  }
+  const bool want_rays = (a.g_rays_o != nullptr) || (a.g_rays_d != nullptr);
+  double gp[3] = {0.0, 0.0, 0.0};
+
+  WarpCtx w;
+  w.lane = threadIdx.x & 31; w.g = w.lane >> 2; w.t = w.lane & 3; w.warp = threadIdx.x >> 5;
+  w.crow = sfeat + w.warp * 32 * RS;
+  w.sG = tiles + w.warp * 1024;
+  w.sG2 = tiles + (WG ? CFG::TILE : 0) + w.warp * 1024;
+  w.sX = tiles + (WG ? 2 * CFG::TILE : 0) + w.warp * 1024;
+  w.sP = sP;
+  w.hs = WG ? a.hscratch + ((size_t)blockIdx.x * CFG::NW + w.warp) * 4096 : nullptr;
+  if (WG) *reinterpret_cast<float4 *>(sP + threadIdx.x * 4) = make_float4(p32[0], p32[1], p32[2], 0.f);
+
+  const float go1[1] = {g_occ};
+  decoder_bwd_mma<STAGE, WG, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+  if (STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR)
+    decoder_bwd_mma<STAGE, WG, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+  if (STAGE == ENS_STAGE_COLOR) {
+    const float go4[4] = {g_rgb[0], g_rgb[1], g_rgb[2], 0.f};            // output 3 is overwritten (decoder.py:341)
+    decoder_bwd_mma<STAGE, WG, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
+  }
+
+  // ---- points -> rays: g_o = sum_s g_p, g_d = sum_s z_s g_p ----
+  if (want_rays) {
+    __syncthreads();
+    sgp[threadIdx.x * 3 + 0] = gp[0]; sgp[threadIdx.x * 3 + 1] = gp[1]; sgp[threadIdx.x * 3 + 2] = gp[2];
+    double *zz = reinterpret_cast<double *>(misc + NT * 24);   // after sgp
+    zz[threadIdx.x] = z;
+    __syncthreads();
+    if (valid && s < 3) {
+      double so = 0.0, sd = 0.0;
+      const int base = threadIdx.x - s;
+      for (int k = 0; k < S; ++k) {
+        const double gk = sgp[(base + k) * 3 + s];
+        so += gk;
+        sd += gk * zz[base + k];
+      }
+      if (a.g_rays_o) a.g_rays_o[ray * 3 + s] = (float)so;
+      if (a.g_rays_d) a.g_rays_d[ray * 3 + s] = (float)sd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int STAGE, bool WG>
+static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
+  using CFG = BwdCfg<STAGE, WG>;
+  a.ra.rpc = CFG::NT / a.ra.S;
+  const size_t smem = CFG::smem_bytes();
+  if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return ENS_ECUDA;
+  const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
+  render_bwd_mma_kernel<STAGE, WG><<<g, CFG::NT, smem, s>>>(a);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s) {
+  switch (stage) {
+    case ENS_STAGE_MIDDLE: return wg ? launch_bwd_mma<ENS_STAGE_MIDDLE, true>(a, s) : launch_bwd_mma<ENS_STAGE_MIDDLE, false>(a, s);
+    case ENS_STAGE_FINE: return wg ? launch_bwd_mma<ENS_STAGE_FINE, true>(a, s) : launch_bwd_mma<ENS_STAGE_FINE, false>(a, s);
+    case ENS_STAGE_COLOR: return wg ? launch_bwd_mma<ENS_STAGE_COLOR, true>(a, s) : launch_bwd_mma<ENS_STAGE_COLOR, false>(a, s);
+    default: return ENS_EUNSUPPORTED;
+  }
+}
+
+// scratch of the WG instantiation: 4 tiles of 4 KB per warp, 6 warps per CTA of 192 / S rays
+int64_t mma_bwd_workspace_bytes(int64_t n_rays, int S) {
+  const int rpc = 192 / S;
+  if (rpc < 1) return 0;
+  const int64_t ctas = (n_rays + rpc - 1) / rpc;
+  return ctas * 6 * 4096 * (int64_t)sizeof(float);
+}
+
+}  // namespace ens

@@ -11,7 +11,14 @@ import numpy as np
 import evennicer_slam_b200.synthetic as syn
 
 SEED = 20                      # run.py:11-20 -- the authors' own setup_seed(20)
-N_TINY_RAYS = 96
+N_TINY_RAYS = 48
+# The relu kink makes the gradient discontinuous: a pre-activation within arithmetic rounding of zero can
+# legitimately land on either side in two correct implementations (torch CPU vs cuBLAS vs the 3xTF32
+# tensor-core path, whose accumulation differs from serial fp32 at the 1e-6 level), and in a 48-ray case ONE
+# flipped unit moves a decoder gradient by > 1e-3.  So every tiny gradient case draws its pixels with the
+# first seed >= SEED whose smallest |pre-activation| (all points, layers, decoders; evaluated with the
+# oracle) exceeds this margin; make_golden.py stores the seed it found as "<tag>.seed".
+TINY_RELU_MARGIN = {"coarse": 3e-6, "middle": 1e-5, "fine": 1e-5, "color": 1e-5}
 N_ROOM0_RAYS = 1000
 # Coarse features are larger: with tiny features the coarse decoder is bias-driven, pre-activations
 # barely vary across points and a whole unit can sit within float rounding of the relu boundary, where
