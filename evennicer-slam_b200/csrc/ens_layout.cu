@@ -51,10 +51,8 @@ __global__ void __launch_bounds__(256) grid_from_native_kernel(const float *__re
 struct PtrTable { const float *p[24]; };
 
 template <int CD, int NO>
-__global__ void pack_mlp_kernel(PtrTable t, float *__restrict__ out) {
+__device__ __forceinline__ void pack_mlp_body(const PtrTable &t, float *__restrict__ out, int idx) {
   using P = MlpPack<CD>;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P::total()) return;
   float v = 0.f;
   // state_dict order: fc_c.i.weight (2i), fc_c.i.bias (2i+1), _B (10), pts.i.weight (11+2i), pts.i.bias (12+2i),
   // out.weight (21), out.bias (22)
@@ -94,10 +92,8 @@ __global__ void pack_mlp_kernel(PtrTable t, float *__restrict__ out) {
 
 // mma layout (see MlpPackV2): dense [out][in], XOR-swizzled columns
 template <int CD, int NO>
-__global__ void pack_mlp_v2_kernel(PtrTable t, float *__restrict__ out) {
+__device__ __forceinline__ void pack_mlp_v2_body(const PtrTable &t, float *__restrict__ out, int idx) {
   using P = MlpPackV2<CD>;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P::total()) return;
   float v = 0.f;
   if (idx < P::off_W0()) {
     int r = idx / EMBP, k = idx % EMBP;
@@ -139,10 +135,8 @@ __global__ void pack_mlp_v2_kernel(PtrTable t, float *__restrict__ out) {
 
 // mma backward layout (see MlpPackV2B): transposed matrices, [in][32], XOR-swizzled columns
 template <int CD, int NO>
-__global__ void pack_mlp_v2b_kernel(PtrTable t, float *__restrict__ out) {
+__device__ __forceinline__ void pack_mlp_v2b_body(const PtrTable &t, float *__restrict__ out, int idx) {
   using P = MlpPackV2B;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P::total()) return;
   float v = 0.f;
   if (idx < P::off_Wo()) {
     int r = idx / EMBP, k = idx % EMBP;
@@ -171,6 +165,17 @@ __global__ void pack_mlp_v2b_kernel(PtrTable t, float *__restrict__ out) {
     }
   }
   out[idx] = v;
+}
+
+// one launch packs all three sections of a decoder blob (fma | mma forward | mma backward)
+template <int CD, int NO>
+__global__ void pack_mlp_all_kernel(PtrTable t, float *__restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < MlpPack<CD>::total()) { pack_mlp_body<CD, NO>(t, out, idx); return; }
+  idx -= MlpPack<CD>::total();
+  if (idx < MlpPackV2<CD>::total()) { pack_mlp_v2_body<CD, NO>(t, out + off_v2<CD>(), idx); return; }
+  idx -= MlpPackV2<CD>::total();
+  if (idx < MlpPackV2B::total()) pack_mlp_v2b_body<CD, NO>(t, out + off_v2b<CD>(), idx);
 }
 
 __global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {
@@ -277,19 +282,13 @@ extern "C" int ens_pack_decoder(int level, const float *const *tensors_host, int
   switch (level) {
     case ENS_LEVEL_COARSE: pack_coarse_kernel<<<nb(CoarsePack::total()), 256, 0, s>>>(t, packed); break;
     case ENS_LEVEL_MIDDLE:
-      pack_mlp_kernel<32, 1><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
-      pack_mlp_v2_kernel<32, 1><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
-      pack_mlp_v2b_kernel<32, 1><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<32>());
+      pack_mlp_all_kernel<32, 1><<<nb(packed_floats(level)), 256, 0, s>>>(t, packed);
       break;
     case ENS_LEVEL_FINE:
-      pack_mlp_kernel<64, 1><<<nb(MlpPack<64>::total()), 256, 0, s>>>(t, packed);
-      pack_mlp_v2_kernel<64, 1><<<nb(MlpPackV2<64>::total()), 256, 0, s>>>(t, packed + MlpPack<64>::total());
-      pack_mlp_v2b_kernel<64, 1><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<64>());
+      pack_mlp_all_kernel<64, 1><<<nb(packed_floats(level)), 256, 0, s>>>(t, packed);
       break;
     default:
-      pack_mlp_kernel<32, 4><<<nb(MlpPack<32>::total()), 256, 0, s>>>(t, packed);
-      pack_mlp_v2_kernel<32, 4><<<nb(MlpPackV2<32>::total()), 256, 0, s>>>(t, packed + MlpPack<32>::total());
-      pack_mlp_v2b_kernel<32, 4><<<nb(MlpPackV2B::total()), 256, 0, s>>>(t, packed + off_v2b<32>());
+      pack_mlp_all_kernel<32, 4><<<nb(packed_floats(level)), 256, 0, s>>>(t, packed);
       break;
   }
   ENS_CHECK_CUDA();

@@ -37,31 +37,38 @@ __device__ __forceinline__ void fast_sincos(float q, float &s, float &c) {
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  // not volatile: the instruction has no side effect beyond d, so ptxas may interleave independent tiles
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // acc[m][nt] += A[m] (16x8, given as hi/lo) * W[8nt..8nt+7][k-tile kt]^T for all four n-tiles; 3xTF32.
-// W: swizzled [32][WROW] in shared memory.
+// W: swizzled [32][WROW] in shared memory.  The three passes (lo.hi, hi.lo, hi.hi) are the OUTER loops, so
+// the eight accumulator tiles give eight independent HMMAs between two dependent ones.
 template <int WROW>
 __device__ __forceinline__ void mma_ktile(float (&acc)[2][4][4], const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4],
                                           const float *__restrict__ W, int kt, int g, int t) {
+  uint32_t bh[4][2], bl[4][2];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     const int n = 8 * nt + g;
     const float2 w = *reinterpret_cast<const float2 *>(W + n * WROW + ((8 * kt + 2 * t) ^ ((g & 3) << 3)));
-    uint32_t bh0, bl0, bh1, bl1;
-    split_tf32(w.x, bh0, bl0);
-    split_tf32(w.y, bh1, bl1);
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      mma_tf32(acc[m][nt], al[m], bh0, bh1);
-      mma_tf32(acc[m][nt], ah[m], bl0, bl1);
-      mma_tf32(acc[m][nt], ah[m], bh0, bh1);
-    }
+    split_tf32(w.x, bh[nt][0], bl[nt][0]);
+    split_tf32(w.y, bh[nt][1], bl[nt][1]);
   }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) mma_tf32(acc[m][nt], al[m], bh[nt][0], bh[nt][1]);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) mma_tf32(acc[m][nt], ah[m], bl[nt][0], bl[nt][1]);
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) mma_tf32(acc[m][nt], ah[m], bh[nt][0], bh[nt][1]);
 }
 
 // A fragments of k-tile kt from an activation held as accumulator fragments x[m][kt][0..3]
@@ -265,12 +272,15 @@ __device__ __forceinline__ void gather_warp(const float *__restrict__ grid, cons
   __syncwarp();
 }
 
+// Copy a packed weight blob global -> shared with cp.async (LDGSTS, 16 bytes per lane, no register round trip):
+// all copies of the CTA are in flight at once; the caller's __syncthreads() (after stage_blob_wait) publishes them.
 __device__ __forceinline__ void stage_blob(float *__restrict__ sw, const float *__restrict__ gw, int nfloats) {
-  const float4 *src = reinterpret_cast<const float4 *>(gw);
-  float4 *dst = reinterpret_cast<float4 *>(sw);
-  for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(sw);
+  for (int i = threadIdx.x; i < nfloats / 4; i += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
-
+__device__ __forceinline__ void stage_blob_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int STAGE> struct MmaStage;
 template <> struct MmaStage<ENS_STAGE_MIDDLE> { static constexpr int RS = 32; static constexpr int WMAX = MlpPackV2<32>::total(); };

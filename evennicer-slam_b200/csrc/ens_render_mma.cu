@@ -32,6 +32,7 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob(sw, sc.w[ENS_LEVEL_MIDDLE] + MlpPack<32>::total(), MlpPackV2<32>::total());
     const Vox v = make_vox(pn, sc.dims[ENS_LEVEL_MIDDLE]);
     gather_warp<RS>(sc.grid[ENS_LEVEL_MIDDLE], sc.dims[ENS_LEVEL_MIDDLE], v, crow, C0);
+    stage_blob_wait();
     __syncthreads();
     float o[1];
     mlp_mma<32, RS, 1>(sw, crow, C0, p32[0], p32[1], p32[2], o);
@@ -42,6 +43,7 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob(sw, sc.w[ENS_LEVEL_FINE] + MlpPack<64>::total(), MlpPackV2<64>::total());
     const Vox v = make_vox(pn, sc.dims[ENS_LEVEL_FINE]);
     gather_warp<RS>(sc.grid[ENS_LEVEL_FINE], sc.dims[ENS_LEVEL_FINE], v, crow, 0);
+    stage_blob_wait();
     __syncthreads();
     float o[1];
     mlp_mma<64, RS, 1>(sw, crow, 0, p32[0], p32[1], p32[2], o);
@@ -52,6 +54,7 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob(sw, sc.w[ENS_LEVEL_COLOR] + MlpPack<32>::total(), MlpPackV2<32>::total());
     const Vox v = make_vox(pn, sc.dims[ENS_LEVEL_COLOR]);
     gather_warp<RS>(sc.grid[ENS_LEVEL_COLOR], sc.dims[ENS_LEVEL_COLOR], v, crow, 0);
+    stage_blob_wait();
     __syncthreads();
     float o[4];
     mlp_mma<32, RS, 4>(sw, crow, 0, p32[0], p32[1], p32[2], o);

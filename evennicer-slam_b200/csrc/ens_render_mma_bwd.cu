@@ -108,16 +108,19 @@ __device__ __forceinline__ void wgrad_mma(float (&d)[NTILES][4], float (&bsum)[2
     split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
     split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
     const float *br0 = B + (pt0 + t) * LDB, *br1 = br0 + 4 * LDB;
+    uint32_t bh[NTILES][2], bl[NTILES][2];
 #pragma unroll
     for (int nt = 0; nt < NTILES; ++nt) {
       const int bc = (bcol0 + 8 * nt + g) ^ sw;
-      uint32_t bh0, bl0, bh1, bl1;
-      split_tf32(br0[bc], bh0, bl0);
-      split_tf32(br1[bc], bh1, bl1);
-      mma_tf32(d[nt], al, bh0, bh1);
-      mma_tf32(d[nt], ah, bl0, bl1);
-      mma_tf32(d[nt], ah, bh0, bh1);
+      split_tf32(br0[bc], bh[nt][0], bl[nt][0]);
+      split_tf32(br1[bc], bh[nt][1], bl[nt][1]);
     }
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(d[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(d[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTILES; ++nt) mma_tf32(d[nt], ah, bh[nt][0], bh[nt][1]);
   }
 }
 
@@ -174,6 +177,12 @@ __device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, 
     const float4 gc = *reinterpret_cast<const float4 *>(crow + src * RS + ((4 * cq) ^ ((src & 3) << 3)));
     const int off0 = b + 4 * cq;
     float gix = 0.f, giy = 0.f, giz = 0.f;
+    float4 a[8];
+    if (want_coord) {       // all eight corner lines in flight before the first use (addresses are always valid)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        a[c] = __ldg(reinterpret_cast<const float4 *>(grid + off0 + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0)));
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const bool inr = (!(c & 1) || (okb & 1u)) && (!(c & 2) || (okb & 2u)) && (!(c & 4) || (okb & 4u));
@@ -185,8 +194,7 @@ __device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, 
           if (w != 0.f) red_add_v4(ggrid + off, w * gc.x, w * gc.y, w * gc.z, w * gc.w);
         }
         if (want_coord) {
-          const float4 a = __ldg(reinterpret_cast<const float4 *>(grid + off));
-          const float dot = fmaf(a.w, gc.w, fmaf(a.z, gc.z, fmaf(a.y, gc.y, a.x * gc.x)));
+          const float dot = fmaf(a[c].w, gc.w, fmaf(a[c].z, gc.z, fmaf(a[c].y, gc.y, a[c].x * gc.x)));
           gix += ((c & 1) ? 1.f : -1.f) * wy * wz * dot;
           giy += ((c & 2) ? 1.f : -1.f) * wx * wz * dot;
           giz += ((c & 4) ? 1.f : -1.f) * wx * wy * dot;
@@ -269,6 +277,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   stage_blob(sw, a.sc.w[LEVEL] + off_v2<CD>(), PF::total());
   const Vox v = make_vox(pn, a.sc.dims[LEVEL]);
   gather_warp<RS>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], v, w.crow, C0);
+  stage_blob_wait();
   __syncthreads();
 
   float rx[4], ry[4], rz[4];
@@ -378,8 +387,9 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   // ---- 3. stage the backward (transposed) blob ----
   __syncthreads();
   stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
-  if (WG) cp_async_tile(w.sX, w.hs + 3 * 1024, lane);                     // x_4 = h_3
+  stage_blob_wait();
   __syncthreads();
+  if (WG) cp_async_tile(w.sX, w.hs + 3 * 1024, lane);                     // x_4 = h_3
 
   // ---- 4. blocks 4..0 ----
   float gc[2][4][4], gu[2][4][4], gu3[2][4][4];

@@ -175,19 +175,31 @@ class _RenderBatchRay(torch.autograd.Function):
         off = 0
         any_param = False
         for gi, lv in enumerate(levels):
-            li = LEVELS.index(lv)
-            if need_grid[gi]:
-                g_native[lv] = torch.zeros_like(ctx.native[lv])
-                grads.grid[li] = g_native[lv].data_ptr()
             n = len(ctx.param_shapes[lv])
             if any(need_param[off:off + n]):
                 any_param = True
             off += n
+        # ONE zero-filled arena for every accumulate-into sink (native grid gradients, flat decoder gradients):
+        # one memset launch instead of one per buffer
+        sizes = []
+        for gi, lv in enumerate(levels):
+            if need_grid[gi]:
+                sizes.append(("g", lv, ctx.native[lv].numel()))
         if any_param:   # the kernel computes decoder grads for all levels of the stage or none
             for lv in levels:
-                li = LEVELS.index(lv)
-                g_flat[lv] = torch.zeros(int(L.ens_decoder_grad_floats(li)), dtype=torch.float32, device=dev)
-                grads.decoder[li] = g_flat[lv].data_ptr()
+                sizes.append(("d", lv, int(L.ens_decoder_grad_floats(LEVELS.index(lv)))))
+        arena = torch.zeros(sum((n + 3) & ~3 for _, _, n in sizes), dtype=torch.float32, device=dev) if sizes else None
+        pos = 0
+        for kind, lv, n in sizes:
+            li = LEVELS.index(lv)
+            view = arena[pos:pos + n]
+            pos += (n + 3) & ~3                       # keep every sink 16-byte aligned (red.global.add.v4)
+            if kind == "g":
+                g_native[lv] = view.view(ctx.native[lv].shape)
+                grads.grid[li] = view.data_ptr()
+            else:
+                g_flat[lv] = view
+                grads.decoder[li] = view.data_ptr()
         g_ro = torch.empty_like(ro) if (need_ro or need_rd) else None
         g_rd = torch.empty_like(rd) if (need_ro or need_rd) else None
         grads.rays_o = g_ro.data_ptr() if g_ro is not None else None
