@@ -44,5 +44,6 @@ def getline(f, ln):
             if p not in src: src[p] = open(p).read().splitlines()
             return src[p][ln - 1].strip()[:110] if 0 < ln <= len(src[p]) else ''
     return ''
-for loc, v in samp.most_common(top):
-    print(f"{100*v/ts:5.1f}% smp {100*ex[loc]/te:5.1f}% ex  {loc[0]}:{loc[1]:<4d} {getline(*loc)}")
+order = ex.most_common(top) if len(sys.argv) > 5 else samp.most_common(top)
+for loc, v in order:
+    print(f"{100*samp[loc]/ts:5.1f}% smp {100*ex[loc]/te:5.1f}% ex  {loc[0]}:{loc[1]:<4d} {getline(*loc)}")
