@@ -371,9 +371,14 @@ def run_gpu_arm(args):
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": eager_ms,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down of a process group whose collectives were captured in a CUDA graph has been seen to hang in
+        # destroy_process_group(); the measurement is complete and printed, so synchronise and leave hard.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def load_traffic():

@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
         a = torch.full((5, 3), float(rank + 1))
         b = torch.full((7,), float(10 * (rank + 1)), dtype=torch.float64)
         c = torch.full((2, 2), float(rank))
-        sh.allreduce_sum_([a, None, b, c], bucket_bytes=64)
+        sh.allreduce_sum_([a, None, b, c], big_bytes=64)
         tot = sum(range(1, world + 1))
         assert torch.all(a == tot) and torch.all(b == 10 * tot) and torch.all(c == sum(range(world)))
         # ragged all-gather
