@@ -19,6 +19,7 @@ STAGE_LEVELS = {"coarse": ("coarse",), "middle": ("middle",), "fine": ("middle",
                 "color": ("middle", "fine", "color")}
 
 ENS_OK = 0
+ABI_VERSION = 2            # include/ens_render.h: ENS_ABI_VERSION
 
 
 class EnsScene(C.Structure):
@@ -47,6 +48,7 @@ _SIGNATURES = {
     "ens_decoder_grad_floats": (C.c_int64, [C.c_int]),
     "ens_decoder_num_tensors": (C.c_int, [C.c_int]),
     "ens_bwd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "ens_fwd_saved_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "ens_grid_to_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ens_grid_from_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ens_pack_decoder": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p]),
@@ -65,10 +67,11 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "ens_render_fwd": (C.c_int, [C.POINTER(EnsScene), C.POINTER(EnsRenderCfg), C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ens_render_bwd": (C.c_int, [C.POINTER(EnsScene), C.POINTER(EnsRenderCfg), C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.POINTER(EnsGrads), C.c_void_p, C.c_int64, C.c_void_p]),
+                                 C.c_void_p, C.POINTER(EnsGrads), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                 C.c_int, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -89,7 +92,7 @@ def lib():
             fn = getattr(handle, name)      # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.ens_version() != 1:
+        if handle.ens_version() != ABI_VERSION:
             raise RuntimeError("libens_render.so ABI version mismatch")
         _lib = handle
     return _lib

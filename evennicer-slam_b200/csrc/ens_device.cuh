@@ -201,11 +201,19 @@ struct FwdArgs {
   float *color;
   double *z_out;
   float *w_out, *raw_out;
+  // saved-for-backward (optional): relu masks [3 decoders][n_tiles][5][32] and activation tiles
+  // [3 decoders][n_tiles][5][1024]; a tile = 32 consecutive sample points
+  uint32_t *save_masks;
+  float *save_h;
+  int64_t n_tiles;
 };
 
 struct BwdArgs {
   DevScene sc;
   RayArgs ra;
+  const uint32_t *save_masks;   // from the forward (null: recompute)
+  const float *save_h;          // from the forward (null: recompute when decoder grads are wanted)
+  int64_t n_tiles;
   const float *raw;
   const double *g_depth, *g_var;
   const float *g_color;
@@ -256,6 +264,7 @@ inline void fill_ray_args(RayArgs &ra, const EnsRenderCfg *cfg, int stage, const
 int mma_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
                     float *out4, cudaStream_t s);
 int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s);
+int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset);
 int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s);
 int64_t mma_bwd_workspace_bytes(int64_t n_rays, int S);
 

@@ -135,13 +135,79 @@ __device__ __forceinline__ void relu_add_bias(float (&acc)[2][4][4], const float
 }
 
 // ---------------------------------------------------------------------------------------------
+// small helpers on accumulator-layout tiles
+// ---------------------------------------------------------------------------------------------
+#define ENS_FOR_TILE(m, nt, e)            \
+  _Pragma("unroll") for (int m = 0; m < 2; ++m) \
+  _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) \
+  _Pragma("unroll") for (int e = 0; e < 4; ++e)
+
+__device__ __forceinline__ void zero_tile(float (&a)[2][4][4]) {
+  ENS_FOR_TILE(m, nt, e) a[m][nt][e] = 0.f;
+}
+
+// acc = relu(acc) + bc ; returns the mask of acc > 0 (bit (m*4+nt)*4+e)
+__device__ __forceinline__ uint32_t relu_add_bias_mask(float (&acc)[2][4][4], const float *__restrict__ bc, int t) {
+  uint32_t mk = 0;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 v = *reinterpret_cast<const float2 *>(bc + 8 * nt + 2 * t);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = acc[m][nt][e];
+        if (a > 0.f) mk |= 1u << ((m * 4 + nt) * 4 + e);
+        acc[m][nt][e] = fmaxf(a, 0.f) + ((e & 1) ? v.y : v.x);
+      }
+    }
+  }
+  return mk;
+}
+
+// store an accumulator-layout tile as a swizzled [32][LD] row-major tile (shared or global):
+// element (row r, col c) at base + r*LD + ((c0 + c) ^ ((r & 3) << 3))
+template <int LD>
+__device__ __forceinline__ void store_tile(float *__restrict__ base, int c0, const float (&x)[2][4][4], int g, int t) {
+  const int sw = (g & 3) << 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = (c0 + 8 * nt + 2 * t) ^ sw;
+      *reinterpret_cast<float2 *>(base + (16 * m + g) * LD + col) = make_float2(x[m][nt][0], x[m][nt][1]);
+      *reinterpret_cast<float2 *>(base + (16 * m + g + 8) * LD + col) = make_float2(x[m][nt][2], x[m][nt][3]);
+    }
+  }
+}
+
+template <int LD>
+__device__ __forceinline__ void load_tile(const float *__restrict__ base, int c0, float (&x)[2][4][4], int g, int t) {
+  const int sw = (g & 3) << 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = (c0 + 8 * nt + 2 * t) ^ sw;
+      const float2 a = *reinterpret_cast<const float2 *>(base + (16 * m + g) * LD + col);
+      const float2 b = *reinterpret_cast<const float2 *>(base + (16 * m + g + 8) * LD + col);
+      x[m][nt][0] = a.x; x[m][nt][1] = a.y; x[m][nt][2] = b.x; x[m][nt][3] = b.y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One Fourier-feature decoder for the warp's 32 points (decoder.py:177-203).
 // sw: MlpPackV2<CD> blob in shared memory.  crow: the warp's feature tile.  (px,py,pz): the OWNER lane's
 // point (p.float()).  Returns the decoder outputs of the owner lane's point in out[NO].
 // ---------------------------------------------------------------------------------------------
-template <int CD, int RS, int NO>
+// SAVE: 0 = nothing; 1 = the five relu masks (one word per lane and block) to msave[i*32]; 2 = masks and the
+// activations h_0..h_4 as swizzled 32x32 tiles to hsave[i*1024..] -- what the backward kernel needs to run without
+// recomputing this forward (ens_render_mma_bwd.cu).
+template <int CD, int RS, int NO, int SAVE = 0>
 __device__ __forceinline__ void mlp_mma(const float *__restrict__ sw, const float *__restrict__ crow, int c0,
-                                        float px, float py, float pz, float (&out)[NO]) {
+                                        float px, float py, float pz, float (&out)[NO],
+                                        uint32_t *__restrict__ msave = nullptr, float *__restrict__ hsave = nullptr) {
   using P = MlpPackV2<CD>;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float rx[4], ry[4], rz[4];                                     // my four rows: points g, g+8, g+16, g+24
@@ -194,8 +260,10 @@ __device__ __forceinline__ void mlp_mma(const float *__restrict__ sw, const floa
       if (i != 3) set_bias(acc, L + P::in_b(), t);
       gemm_hidden(acc, x, L + P::in_Wh(), g, t);
     }
-    relu_add_bias(acc, L + P::in_bc(), t);
+    if (SAVE) msave[i * 32] = relu_add_bias_mask(acc, L + P::in_bc(), t);
+    else relu_add_bias(acc, L + P::in_bc(), t);
     gemm_features<CD, RS>(acc, crow, c0, L + P::in_Wc(), g, t);
+    if (SAVE == 2) store_tile<32>(hsave + i * 1024, 0, acc, g, t);
   }
   // ---- output layer on the FMA pipe: per-lane partial dot over its 8 features, quad reduce ----
   float part[4][NO];

@@ -890,6 +890,11 @@ static bool use_mma_forward() {
   return !(v && std::strcmp(v, "fma") == 0);
 }
 
+static bool use_mma_backward() {
+  const char *v = std::getenv("ENS_BWD_VARIANT");
+  return !(v && std::strcmp(v, "fma") == 0);
+}
+
 extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_is_f64, int64_t n,
                                int apply_bound_mask, float *out4, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
@@ -914,7 +919,7 @@ extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts
 extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                               const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                               double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,
-                              ens_stream_t stream) {
+                              void *saved, int64_t saved_bytes, int saved_with_activations, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
   if (!rays_o || !rays_d || !depth || !var || !color || n_rays < 0) return ENS_EINVAL;
@@ -928,6 +933,17 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   a.sc = make_dev_scene(scene);
   fill_ray_args(a.ra, cfg, stage, rays_o, rays_d, gt_depth, depth_max, n_rays, S, ns);
   a.depth = depth; a.var = var; a.color = color; a.z_out = z_vals; a.w_out = weights; a.raw_out = raw;
+  a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0;
+  if (saved != nullptr) {
+    int64_t n_tiles = 0, h_off = 0;
+    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, saved_with_activations, &n_tiles, &h_off);
+    if (need > 0) {
+      if (saved_bytes < need || (reinterpret_cast<uintptr_t>(saved) & 15)) return ENS_ESHAPE;
+      a.save_masks = reinterpret_cast<uint32_t *>(saved);
+      a.save_h = saved_with_activations ? reinterpret_cast<float *>(reinterpret_cast<char *>(saved) + h_off) : nullptr;
+      a.n_tiles = n_tiles;
+    }
+  }
   cudaStream_t s = (cudaStream_t)stream;
   if (use_mma_forward()) {
     rc = mma_render_fwd(a, stage, s);
@@ -941,9 +957,9 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   }
 }
 
-static bool use_mma_backward() {
-  const char *v = std::getenv("ENS_BWD_VARIANT");
-  return !(v && std::strcmp(v, "fma") == 0);
+extern "C" int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int stage, int want_decoder_grads) {
+  if (!use_mma_forward() || !use_mma_backward()) return 0;
+  return mma_fwd_saved_bytes(n_rays, n_samples_total, stage, want_decoder_grads, nullptr, nullptr);
 }
 
 extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads) {
@@ -956,7 +972,8 @@ extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, 
 extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                               const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                               const float *raw, const double *g_depth, const double *g_var, const float *g_color,
-                              const EnsGrads *grads, void *workspace, int64_t workspace_bytes, ens_stream_t stream) {
+                              const EnsGrads *grads, void *workspace, int64_t workspace_bytes, const void *saved,
+                              int64_t saved_bytes, int saved_with_activations, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
   if (!rays_o || !rays_d || !raw || !grads || n_rays < 0) return ENS_EINVAL;
@@ -985,7 +1002,19 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   wg = n_dec > 0;
   a.g_rays_o = grads->rays_o; a.g_rays_d = grads->rays_d;
   a.hscratch = (float *)workspace;
-  if (wg) {
+  a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0;
+  if (saved != nullptr && use_mma_backward()) {
+    int64_t n_tiles = 0, h_off = 0;
+    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, saved_with_activations, &n_tiles, &h_off);
+    if (need > 0) {
+      if (saved_bytes < need) return ENS_ESHAPE;
+      a.save_masks = reinterpret_cast<const uint32_t *>(saved);
+      a.save_h = saved_with_activations ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(saved) + h_off) : nullptr;
+      a.n_tiles = n_tiles;
+    }
+  }
+  const bool saved_covers = a.save_masks != nullptr && (!wg || a.save_h != nullptr);
+  if (wg && !saved_covers) {
     if (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1)) return ENS_ESHAPE;
   }
   cudaStream_t s = (cudaStream_t)stream;

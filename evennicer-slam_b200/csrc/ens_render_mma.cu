@@ -20,10 +20,12 @@
 namespace ens {
 
 // NICE.forward for the owner lane's point (decoder.py:312-342).  CTA-collective.
-// sw: weight region; sfeat: the CTA's [NT][RS] feature tile.
-template <int STAGE>
+// sw: weight region; sfeat: the CTA's [NT][RS] feature tile.  SAVE / msave / hsave: see mlp_mma; the pointers address
+// this warp's tile of decoder 0 (middle); decoder d lives dstride_m words / dstride_h floats further.
+template <int STAGE, int SAVE = 0>
 __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__restrict__ sw, float *__restrict__ sfeat,
-                                                   const float pn[3], const float p32[3]) {
+                                                   const float pn[3], const float p32[3], uint32_t *msave = nullptr,
+                                                   float *hsave = nullptr, int64_t dstride_m = 0, int64_t dstride_h = 0) {
   constexpr int RS = MmaStage<STAGE>::RS;
   float *crow = sfeat + (threadIdx.x >> 5) * 32 * RS;             // this warp's 32 rows
   float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -35,7 +37,7 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob_wait();
     __syncthreads();
     float o[1];
-    mlp_mma<32, RS, 1>(sw, crow, C0, p32[0], p32[1], p32[2], o);
+    mlp_mma<32, RS, 1, SAVE>(sw, crow, C0, p32[0], p32[1], p32[2], o, msave, hsave);
     raw.w = o[0];
   }
   if (STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR) {
@@ -46,7 +48,8 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob_wait();
     __syncthreads();
     float o[1];
-    mlp_mma<64, RS, 1>(sw, crow, 0, p32[0], p32[1], p32[2], o);
+    mlp_mma<64, RS, 1, SAVE>(sw, crow, 0, p32[0], p32[1], p32[2], o, SAVE ? msave + dstride_m : nullptr,
+                             SAVE == 2 ? hsave + dstride_h : nullptr);
     raw.w = __fadd_rn(o[0], raw.w);                               // fine_occ + middle_occ
   }
   if (STAGE == ENS_STAGE_COLOR) {
@@ -57,7 +60,8 @@ __device__ __forceinline__ float4 decode_stage_mma(const DevScene &sc, float *__
     stage_blob_wait();
     __syncthreads();
     float o[4];
-    mlp_mma<32, RS, 4>(sw, crow, 0, p32[0], p32[1], p32[2], o);
+    mlp_mma<32, RS, 4, SAVE>(sw, crow, 0, p32[0], p32[1], p32[2], o, SAVE ? msave + 2 * dstride_m : nullptr,
+                             SAVE == 2 ? hsave + 2 * dstride_h : nullptr);
     raw.x = o[0]; raw.y = o[1]; raw.z = o[2];
   }
   return raw;
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(NT_MMA) eval_points_mma_kernel(DevScene sc, co
 // ---------------------------------------------------------------------------------------------
 // render forward (mma): same structure as the fma variant, different decode
 // ---------------------------------------------------------------------------------------------
-template <int STAGE>
+template <int STAGE, int SAVE>
 __global__ void __launch_bounds__(NT_MMA) render_fwd_mma_kernel(FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NT = NT_MMA;
@@ -132,7 +136,12 @@ __global__ void __launch_bounds__(NT_MMA) render_fwd_mma_kernel(FwdArgs a) {
     inside &= (p[k] < a.sc.hi[k]) && (p[k] > a.sc.lo[k]);
   }
   normalize64(p, a.sc.lo, a.sc.hi, pn);
-  float4 raw = decode_stage_mma<STAGE>(a.sc, sw, sfeat, pn, p32);
+  // saved-for-backward tile of this warp: 32 consecutive points starting at blockIdx.x * NT + warp * 32
+  // (the launcher only enables SAVE when NT is a multiple of S, so CTA b owns points [b*NT, (b+1)*NT))
+  const int64_t tile = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  uint32_t *msave = SAVE ? a.save_masks + tile * 160 + (threadIdx.x & 31) : nullptr;
+  float *hsave = SAVE == 2 ? a.save_h + tile * 5120 : nullptr;
+  float4 raw = decode_stage_mma<STAGE, SAVE>(a.sc, sw, sfeat, pn, p32, msave, hsave, a.n_tiles * 160, a.n_tiles * 5120);
   if (!inside) raw.w = 100.f;
   // ---- compositing (common.py:285-296) ----
   const float alpha = 1.f / (1.f + expf(-(10.f * raw.w)));
@@ -207,25 +216,48 @@ int mma_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f
   }
 }
 
-template <int STAGE>
+template <int STAGE, int SAVE>
 static int launch_fwd_mma(FwdArgs &a, cudaStream_t s) {
   constexpr int NT = NT_MMA;
   a.ra.rpc = NT / a.ra.S;
   const size_t smem = (size_t)(MmaStage<STAGE>::WMAX + NT * MmaStage<STAGE>::RS) * 4 + (size_t)NT * (8 + 8 + 16 + 4 + 4);
-  if (cudaFuncSetAttribute(render_fwd_mma_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  if (cudaFuncSetAttribute(render_fwd_mma_kernel<STAGE, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
-  render_fwd_mma_kernel<STAGE><<<g, NT, smem, s>>>(a);
+  render_fwd_mma_kernel<STAGE, SAVE><<<g, NT, smem, s>>>(a);
   ENS_CHECK_CUDA();
   return ENS_OK;
 }
 
+template <int STAGE>
+static int launch_fwd_mma_save(FwdArgs &a, cudaStream_t s) {
+  const int save = (a.save_masks != nullptr && (192 % a.ra.S) == 0) ? (a.save_h != nullptr ? 2 : 1) : 0;
+  switch (save) {
+    case 2: return launch_fwd_mma<STAGE, 2>(a, s);
+    case 1: return launch_fwd_mma<STAGE, 1>(a, s);
+    default: return launch_fwd_mma<STAGE, 0>(a, s);
+  }
+}
+
 int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s) {
   switch (stage) {
-    case ENS_STAGE_MIDDLE: return launch_fwd_mma<ENS_STAGE_MIDDLE>(a, s);
-    case ENS_STAGE_FINE: return launch_fwd_mma<ENS_STAGE_FINE>(a, s);
-    case ENS_STAGE_COLOR: return launch_fwd_mma<ENS_STAGE_COLOR>(a, s);
+    case ENS_STAGE_MIDDLE: return launch_fwd_mma_save<ENS_STAGE_MIDDLE>(a, s);
+    case ENS_STAGE_FINE: return launch_fwd_mma_save<ENS_STAGE_FINE>(a, s);
+    case ENS_STAGE_COLOR: return launch_fwd_mma_save<ENS_STAGE_COLOR>(a, s);
     default: return ENS_EUNSUPPORTED;
   }
+}
+
+// Bytes of the saved-for-backward buffer of the mma forward, 0 if the fast path does not apply (coarse stage, or a
+// samples-per-ray count that does not tile the CTAs).  Layout: masks u32 [3][n_tiles][5][32], then (want_h)
+// activations f32 [3][n_tiles][5][1024] at *h_offset bytes.
+int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset) {
+  if (stage == ENS_STAGE_COARSE || S < 1 || (192 % S) != 0 || n_rays <= 0) return 0;
+  const int rpc = NT_MMA / S;
+  const int64_t tiles = ((n_rays + rpc - 1) / rpc) * (NT_MMA / 32);
+  const int64_t mbytes = 3 * tiles * 160 * 4;
+  if (n_tiles) *n_tiles = tiles;
+  if (h_offset) *h_offset = mbytes;
+  return mbytes + (want_h ? 3 * tiles * 5120 * 4 : 0);
 }
 
 }  // namespace ens

@@ -28,53 +28,6 @@
 
 namespace ens {
 
-// ---------------------------------------------------------------------------------------------
-// small helpers on accumulator-layout tiles
-// ---------------------------------------------------------------------------------------------
-#define ENS_FOR_TILE(m, nt, e)            \
-  _Pragma("unroll") for (int m = 0; m < 2; ++m) \
-  _Pragma("unroll") for (int nt = 0; nt < 4; ++nt) \
-  _Pragma("unroll") for (int e = 0; e < 4; ++e)
-
-__device__ __forceinline__ void zero_tile(float (&a)[2][4][4]) {
-  ENS_FOR_TILE(m, nt, e) a[m][nt][e] = 0.f;
-}
-
-// acc = relu(acc) + bc ; returns the mask of acc > 0 (bit (m*4+nt)*4+e)
-__device__ __forceinline__ uint32_t relu_add_bias_mask(float (&acc)[2][4][4], const float *__restrict__ bc, int t) {
-  uint32_t mk = 0;
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    const float2 v = *reinterpret_cast<const float2 *>(bc + 8 * nt + 2 * t);
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float a = acc[m][nt][e];
-        if (a > 0.f) mk |= 1u << ((m * 4 + nt) * 4 + e);
-        acc[m][nt][e] = fmaxf(a, 0.f) + ((e & 1) ? v.y : v.x);
-      }
-    }
-  }
-  return mk;
-}
-
-// store an accumulator-layout tile as a swizzled [32][LD] row-major tile (shared or global):
-// element (row r, col c) at base + r*LD + ((c0 + c) ^ ((r & 3) << 3))
-template <int LD>
-__device__ __forceinline__ void store_tile(float *__restrict__ base, int c0, const float (&x)[2][4][4], int g, int t) {
-  const int sw = (g & 3) << 3;
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = (c0 + 8 * nt + 2 * t) ^ sw;
-      *reinterpret_cast<float2 *>(base + (16 * m + g) * LD + col) = make_float2(x[m][nt][0], x[m][nt][1]);
-      *reinterpret_cast<float2 *>(base + (16 * m + g + 8) * LD + col) = make_float2(x[m][nt][2], x[m][nt][3]);
-    }
-  }
-}
-
 // asynchronous 4 KB tile copy global -> shared by one warp (no registers)
 __device__ __forceinline__ void cp_async_tile(float *__restrict__ sdst, const float *__restrict__ gsrc, int lane) {
   const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(sdst);
@@ -221,12 +174,14 @@ __device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, 
 // ---------------------------------------------------------------------------------------------
 // kernel configuration
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG>
+// RECOMP = true: the forward saved nothing usable, recompute it here (steps 1-2 above).  RECOMP = false: relu masks
+// (and, for WG, the activation tiles h_0..h_4) come from the buffer the forward kernel wrote.
+template <int STAGE, bool WG, bool RECOMP>
 struct BwdCfg {
-  static constexpr int NT = WG ? 192 : 256;
+  static constexpr int NT = (WG || !RECOMP) ? 192 : 256;
   static constexpr int NW = NT / 32;
   static constexpr int RS = MmaStage<STAGE>::RS;
-  static constexpr int WREG = MmaStage<STAGE>::WMAX;                    // >= MlpPackV2B::total()
+  static constexpr int WREG = RECOMP ? MmaStage<STAGE>::WMAX : MlpPackV2B::total();   // forward blob >= backward blob
   static constexpr int TILE = NT * 32;                                  // floats of one staging tile
   static constexpr int NTILES = WG ? 3 : 0;                             // sG, sG2, sX
   static constexpr int MISC_BYTES = NT * 56;                            // placement / compositing scratch, later sgp
@@ -247,7 +202,8 @@ struct WarpCtx {
   float *crow;       // warp's feature-tile rows
   float *sG, *sG2, *sX;   // CTA tiles (WG)
   float *sP;         // [NT][4] points (WG)
-  float *hs;         // global scratch of this warp: 4 tiles of 1024 floats (WG)
+  float *hs;         // RECOMP: global scratch of this warp, 4 tiles of 1024 floats (WG)
+  int64_t gtile;     // global index of this warp's 32-point tile (saved-for-backward layout)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -256,13 +212,14 @@ struct WarpCtx {
 //   p32        : owner lane's p.float();  pn: its normalised coordinates
 //   gp         : owner lane's accumulated d L / d p (float64)
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG, int LEVEL, int CD, int NO>
+template <int STAGE, bool WG, bool RECOMP, int LEVEL, int CD, int NO>
 __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restrict__ sw, const WarpCtx &w,
                                                 const float pn[3], const float p32[3], const float (&gout)[NO],
                                                 bool valid, bool want_rays, double gp[3]) {
-  using CFG = BwdCfg<STAGE, WG>;
+  using CFG = BwdCfg<STAGE, WG, RECOMP>;
   constexpr int RS = CFG::RS;
   constexpr int NT = CFG::NT;
+  constexpr int DEC = (LEVEL == ENS_LEVEL_MIDDLE) ? 0 : (LEVEL == ENS_LEVEL_FINE ? 1 : 2);
   using PF = MlpPackV2<CD>;
   using PB = MlpPackV2B;
   using GO = MlpGrad<CD, NO>;
@@ -272,11 +229,14 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   float *ggrid = a.ggrid[LEVEL];
   const bool need_emb = WG || want_rays;
 
-  // ---- 1. stage the forward blob, gather features ----
+  // ---- 1. stage the weights (RECOMP: forward blob; otherwise directly the transposed blob), gather features ----
+  // activation tiles h_0..h_4 of this warp: own scratch when recomputed, else what the forward saved
+  const float *hsrc = RECOMP ? w.hs : (WG ? a.save_h + ((int64_t)DEC * a.n_tiles + w.gtile) * 5120 : nullptr);
   __syncthreads();
-  stage_blob(sw, a.sc.w[LEVEL] + off_v2<CD>(), PF::total());
+  if (RECOMP) stage_blob(sw, a.sc.w[LEVEL] + off_v2<CD>(), PF::total());
+  else stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
   const Vox v = make_vox(pn, a.sc.dims[LEVEL]);
-  gather_warp<RS>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], v, w.crow, C0);
+  if (RECOMP || WG) gather_warp<RS>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], v, w.crow, C0);   // features: recompute / dWc operand
   stage_blob_wait();
   __syncthreads();
 
@@ -292,7 +252,9 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   uint32_t mask[5];
   float gh[2][4][4];
   {
-    float acc[2][4][4], acc3[2][4][4];
+    float acc[2][4][4];
+    if (RECOMP) {
+    float acc3[2][4][4];
     set_bias(acc, sw + PF::off_L(0) + PF::in_b(), t);
     set_bias(acc3, sw + PF::off_L(3) + PF::in_b(), t);
 #pragma unroll 1
@@ -334,6 +296,12 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
       gemm_features<CD, RS>(acc, w.crow, C0 == 32 ? 32 : 0, L + PF::in_Wc(), g, t);
       if (WG && i < 4) store_tile<32>(w.hs + i * 1024, 0, acc, g, t);      // h_i = x_{i+1}
     }
+    } else {
+      const uint32_t *ms = a.save_masks + (((int64_t)DEC * a.n_tiles + w.gtile) * 5) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) mask[k] = ms[k * 32];
+      if (WG) load_tile<32>(hsrc + 4 * 1024, 0, acc, g, t);                 // h_4 for dWo
+    }
     // decoder-output gradients of my four rows
     float gr[4][NO];
 #pragma unroll
@@ -369,7 +337,8 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
     for (int nt = 0; nt < 4; ++nt) {
       float2 wo[NO];
 #pragma unroll
-      for (int o = 0; o < NO; ++o) wo[o] = *reinterpret_cast<const float2 *>(sw + PF::off_Wo() + o * 32 + 8 * nt + 2 * t);
+      for (int o = 0; o < NO; ++o)
+        wo[o] = *reinterpret_cast<const float2 *>(sw + (RECOMP ? PF::off_Wo() : PB::off_Wo()) + o * 32 + 8 * nt + 2 * t);
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
 #pragma unroll
@@ -385,11 +354,13 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   }
 
   // ---- 3. stage the backward (transposed) blob ----
-  __syncthreads();
-  stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
-  stage_blob_wait();
-  __syncthreads();
-  if (WG) cp_async_tile(w.sX, w.hs + 3 * 1024, lane);                     // x_4 = h_3
+  if (RECOMP) {
+    __syncthreads();
+    stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
+    stage_blob_wait();
+    __syncthreads();
+  }
+  if (WG) cp_async_tile(w.sX, hsrc + 3 * 1024, lane);                     // x_4 = h_3
 
   // ---- 4. blocks 4..0 ----
   float gc[2][4][4], gu[2][4][4], gu3[2][4][4];
@@ -441,7 +412,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
         emit_strip<4>(out, CD, 32, 32, m, d, g, t);
       }
       __syncthreads();
-      if (i >= 2) cp_async_tile(w.sX, w.hs + (i - 2) * 1024, lane);       // x_{i-1} = h_{i-2}
+      if (i >= 2) cp_async_tile(w.sX, hsrc + (i - 2) * 1024, lane);       // x_{i-1} = h_{i-2}
     }
   }
   // gu = g_u0 (registers; WG: also in sG2), gu3 = g_u3.
@@ -577,9 +548,9 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG>
-__global__ void __launch_bounds__(BwdCfg<STAGE, WG>::NT, 1) render_bwd_mma_kernel(BwdArgs a) {
-  using CFG = BwdCfg<STAGE, WG>;
+template <int STAGE, bool WG, bool RECOMP>
+__global__ void __launch_bounds__(BwdCfg<STAGE, WG, RECOMP>::NT, 1) render_bwd_mma_kernel(BwdArgs a) {
+  using CFG = BwdCfg<STAGE, WG, RECOMP>;
   constexpr int NT = CFG::NT;
   constexpr int RS = CFG::RS;
   extern __shared__ __align__(16) float smem[];
@@ -680,16 +651,17 @@ __global__ void __launch_bounds__(BwdCfg<STAGE, WG>::NT, 1) render_bwd_mma_kerne
   w.sG2 = tiles + (WG ? CFG::TILE : 0) + w.warp * 1024;
   w.sX = tiles + (WG ? 2 * CFG::TILE : 0) + w.warp * 1024;
   w.sP = sP;
-  w.hs = WG ? a.hscratch + ((size_t)blockIdx.x * CFG::NW + w.warp) * 4096 : nullptr;
+  w.hs = (WG && RECOMP) ? a.hscratch + ((size_t)blockIdx.x * CFG::NW + w.warp) * 4096 : nullptr;
+  w.gtile = (int64_t)blockIdx.x * CFG::NW + w.warp;
   if (WG) *reinterpret_cast<float4 *>(sP + threadIdx.x * 4) = make_float4(p32[0], p32[1], p32[2], 0.f);
 
   const float go1[1] = {g_occ};
-  decoder_bwd_mma<STAGE, WG, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+  decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
   if (STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR)
-    decoder_bwd_mma<STAGE, WG, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+    decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
   if (STAGE == ENS_STAGE_COLOR) {
     const float go4[4] = {g_rgb[0], g_rgb[1], g_rgb[2], 0.f};            // output 3 is overwritten (decoder.py:341)
-    decoder_bwd_mma<STAGE, WG, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
+    decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
   }
 
   // ---- points -> rays: g_o = sum_s g_p, g_d = sum_s z_s g_p ----
@@ -716,24 +688,33 @@ __global__ void __launch_bounds__(BwdCfg<STAGE, WG>::NT, 1) render_bwd_mma_kerne
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG>
+template <int STAGE, bool WG, bool RECOMP>
 static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
-  using CFG = BwdCfg<STAGE, WG>;
+  using CFG = BwdCfg<STAGE, WG, RECOMP>;
   a.ra.rpc = CFG::NT / a.ra.S;
   const size_t smem = CFG::smem_bytes();
-  if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ENS_ECUDA;
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
-  render_bwd_mma_kernel<STAGE, WG><<<g, CFG::NT, smem, s>>>(a);
+  render_bwd_mma_kernel<STAGE, WG, RECOMP><<<g, CFG::NT, smem, s>>>(a);
   ENS_CHECK_CUDA();
   return ENS_OK;
 }
 
+template <int STAGE>
+static int launch_bwd_mma_any(BwdArgs &a, bool wg, cudaStream_t s) {
+  // the saved-forward fast path needs the masks, the activation tiles when decoder gradients are wanted, and a
+  // samples-per-ray count that tiles the 192-thread CTAs (so forward and backward agree on the 32-point tiles)
+  const bool saved = a.save_masks != nullptr && (192 % a.ra.S) == 0 && (!wg || a.save_h != nullptr);
+  if (saved) return wg ? launch_bwd_mma<STAGE, true, false>(a, s) : launch_bwd_mma<STAGE, false, false>(a, s);
+  return wg ? launch_bwd_mma<STAGE, true, true>(a, s) : launch_bwd_mma<STAGE, false, true>(a, s);
+}
+
 int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s) {
   switch (stage) {
-    case ENS_STAGE_MIDDLE: return wg ? launch_bwd_mma<ENS_STAGE_MIDDLE, true>(a, s) : launch_bwd_mma<ENS_STAGE_MIDDLE, false>(a, s);
-    case ENS_STAGE_FINE: return wg ? launch_bwd_mma<ENS_STAGE_FINE, true>(a, s) : launch_bwd_mma<ENS_STAGE_FINE, false>(a, s);
-    case ENS_STAGE_COLOR: return wg ? launch_bwd_mma<ENS_STAGE_COLOR, true>(a, s) : launch_bwd_mma<ENS_STAGE_COLOR, false>(a, s);
+    case ENS_STAGE_MIDDLE: return launch_bwd_mma_any<ENS_STAGE_MIDDLE>(a, wg, s);
+    case ENS_STAGE_FINE: return launch_bwd_mma_any<ENS_STAGE_FINE>(a, wg, s);
+    case ENS_STAGE_COLOR: return launch_bwd_mma_any<ENS_STAGE_COLOR>(a, wg, s);
     default: return ENS_EUNSUPPORTED;
   }
 }

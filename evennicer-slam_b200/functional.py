@@ -15,6 +15,7 @@ from ._lib import LEVELS, STAGES, STAGE_LEVELS, EnsGrads, EnsRenderCfg
 from .scene import SceneCache, build_scene_struct, decoder_grad_views
 
 
+SAVE_FORWARD = True    # keep relu masks / activations from the forward kernel for the backward (False: it recomputes)
 _DEBUG: Dict[str, object] = {}     # test hook: set _DEBUG["keep_workspace"]=True to inspect the backward scratch
 
 
@@ -135,11 +136,24 @@ class _RenderBatchRay(torch.autograd.Function):
         z = torch.empty((R, S), dtype=torch.float64, device=dev) if want_aux else None
         w = torch.empty((R, S), dtype=torch.float32, device=dev) if want_aux else None
         gd = _f32c(gt_depth).reshape(-1) if has_depth else None
+        # saved-for-backward state (what autograd keeps as saved tensors in the reference): relu masks, and the
+        # hidden activations when a decoder parameter wants gradient -- the backward then skips the recompute
+        needs = ctx.needs_input_grad
+        want_bwd = any(needs[6:])
+        want_dec = want_bwd and any(needs[8 + n_grids:])
+        saved = None
+        if want_bwd and SAVE_FORWARD:
+            nbytes = int(L.ens_fwd_saved_bytes(R, S, STAGES[setup.stage], int(want_dec)))
+            if nbytes > 0:
+                saved = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
         stream = _lib.cur_stream(dev)
         _lib.check(TIMER.launch("render_fwd", dev, lambda: L.ens_render_fwd(
             C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd),
             _lib.ptr(depth_max) if has_depth else None, R, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color),
-            _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), stream)), "ens_render_fwd")
+            _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0,
+            int(want_dec), stream)), "ens_render_fwd")
+        ctx.saved_fwd = saved
+        ctx.saved_has_h = bool(want_dec)
         ctx.setup = setup
         ctx.levels = levels
         ctx.n_grids = n_grids
@@ -204,7 +218,10 @@ class _RenderBatchRay(torch.autograd.Function):
         g_rd = torch.empty_like(rd) if (need_ro or need_rd) else None
         grads.rays_o = g_ro.data_ptr() if g_ro is not None else None
         grads.rays_d = g_rd.data_ptr() if g_rd is not None else None
-        ws_bytes = int(L.ens_bwd_workspace_bytes(R, S, 1 if any_param else 0))
+        saved = ctx.saved_fwd
+        if saved is not None and any_param and not ctx.saved_has_h:
+            saved = None                      # activations were not kept: let the kernel recompute
+        ws_bytes = 0 if saved is not None else int(L.ens_bwd_workspace_bytes(R, S, 1 if any_param else 0))
         ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
         sc = build_scene_struct(setup.bound, setup.coarse_bound, ctx.native, ctx.packed)
         cfg = setup.cfg_struct()
@@ -216,6 +233,7 @@ class _RenderBatchRay(torch.autograd.Function):
             C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd),
             _lib.ptr(gd) if ctx.has_depth else None, _lib.ptr(depth_max) if ctx.has_depth else None, R,
             _lib.ptr(raw), _lib.ptr(gdp), _lib.ptr(gvp), _lib.ptr(gcp), C.byref(grads), _lib.ptr(ws), ws_bytes,
+            _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0, int(ctx.saved_has_h),
             stream)), "ens_render_bwd")
         if _DEBUG.get("keep_workspace"):
             _DEBUG["workspace"] = ws

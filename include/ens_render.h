@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ENS_ABI_VERSION 1
+#define ENS_ABI_VERSION 2
 
 typedef void *ens_stream_t; /* cudaStream_t */
 
@@ -97,6 +97,10 @@ int64_t ens_decoder_grad_floats(int level);
 int ens_decoder_num_tensors(int level);
 /* bytes of scratch ens_render_bwd needs for R rays x S samples when decoder grads are requested */
 int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads);
+/* bytes of the saved-for-backward buffer ens_render_fwd can fill (relu masks, plus the hidden activations when
+ * decoder gradients will be wanted) so that ens_render_bwd does not recompute the forward -- what torch autograd
+ * keeps as saved tensors in the reference.  0 = not applicable for this stage / sample count (pass NULL). */
+int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int stage, int want_decoder_grads);
 
 /* [32][Z][Y][X] -> [Z][Y][X][32]  and back.  n_vox = Z*Y*X.  (layout of `c`, EvenNICER_SLAM.py:217-275) */
 int ens_grid_to_native(const float *ref_layout, float *native, int64_t n_vox, ens_stream_t stream);
@@ -152,20 +156,24 @@ int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_i
  * (src/common.py:256-297).  gt_depth may be NULL (and is ignored for stage coarse); depth_max is the
  * device double[2] from ens_depth_max (NULL iff gt_depth is NULL).
  * Outputs: depth f64 [R], var f64 [R], color f32 [R][3].  Optional (may be NULL): z_vals f64 [R][S],
- * weights f32 [R][S], raw f32 [R][S][4] (pre-sigmoid; `raw` is also what ens_render_bwd wants back). */
+ * weights f32 [R][S], raw f32 [R][S][4] (pre-sigmoid; `raw` is also what ens_render_bwd wants back).
+ * saved / saved_bytes: optional buffer of ens_fwd_saved_bytes(n_rays, S, stage, saved_with_activations) bytes,
+ * filled for ens_render_bwd (16-byte aligned; NULL = the backward recomputes). */
 int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                    const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                    double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,
-                   ens_stream_t stream);
+                   void *saved, int64_t saved_bytes, int saved_with_activations, ens_stream_t stream);
 
 /* Backward of ens_render_fwd into grid features, decoder weights and rays.
  * Recomputes sample placement and activations; `raw` is the [R][S][4] tensor saved by the forward.
  * g_depth f64 [R], g_var f64 [R], g_color f32 [R][3]; any may be NULL (= zero).
- * workspace: ens_bwd_workspace_bytes bytes (only touched when decoder grads are requested). */
+ * workspace: ens_bwd_workspace_bytes bytes (only touched when decoder grads are requested and nothing was saved).
+ * saved / saved_bytes / saved_with_activations: the buffer ens_render_fwd filled for the same rays (or NULL). */
 int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                    const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                    const float *raw, const double *g_depth, const double *g_var, const float *g_color,
-                   const EnsGrads *grads, void *workspace, int64_t workspace_bytes, ens_stream_t stream);
+                   const EnsGrads *grads, void *workspace, int64_t workspace_bytes, const void *saved,
+                   int64_t saved_bytes, int saved_with_activations, ens_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@ def tiny():
 def test_library_loads_and_reports_version():
     from evennicer_slam_b200 import _lib
     L = _lib.lib()
-    assert L.ens_version() == 1
+    assert L.ens_version() == 2
     assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 and L.ens_decoder_grad_floats(3) == 15899
 
 
@@ -176,6 +176,31 @@ def test_render_backward(tiny, stage, use_depth):
     for lv in STAGES:   # untouched levels get no gradient
         if lv not in orc.STAGE_DECODERS[stage]:
             assert cg["grid_" + lv].grad is None
+
+
+@pytest.mark.parametrize("stage,use_depth", [("color", True), ("fine", False), ("middle", True)])
+def test_render_backward_recompute_path(tiny, stage, use_depth):
+    """The backward kernels also run WITHOUT the forward's saved masks / activations (direct C-ABI callers that pass
+    saved = NULL): they then recompute the forward in-kernel.  Same gradients, same tolerance."""
+    from evennicer_slam_b200 import functional
+    g, decoders = tiny["g"], tiny["decoders"]
+    functional.SAVE_FORWARD = False
+    try:
+        tag, cg, ro, rd, (depth, var, color, raw, z, w) = _run_case(tiny, stage, use_depth)
+        g_d, g_v, g_c = cases.upstream_grads(ro.shape[0])
+        ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+         + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    finally:
+        functional.SAVE_FORWARD = True
+    assert rel_err(ro.grad.cpu().numpy(), g[f"{tag}.g_rays_o"]) < TOL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), g[f"{tag}.g_rays_d"]) < TOL_GRAD
+    for name in orc.STAGE_DECODERS[stage]:
+        gk = "grid_" + name
+        assert rel_err(cg[gk].grad.cpu().numpy(), g[f"{tag}.ggrid.{gk}"]) < TOL_GRAD, gk
+        for key, p in getattr(decoders, name + "_decoder").named_parameters():
+            ref = g[f"{tag}.gdec.{name}.{key}"]
+            if np.abs(ref).max() > 0:
+                assert rel_err(p.grad.cpu().numpy(), ref) < TOL_GRAD, (name, key)
 
 
 def test_backward_without_decoder_or_grid_grads_matches(tiny):
