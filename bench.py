@@ -44,6 +44,15 @@ BYTES_PER_POINT_BWD = 1024 * 3 + 1024 * 3       # re-gather + scatter-add
 BYTES_PER_RAY = (BYTES_PER_POINT_FWD + BYTES_PER_POINT_BWD) * S_TOTAL   # 442 368
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -212,7 +221,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config():
@@ -371,7 +380,7 @@ def run_gpu_arm(args):
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": eager_ms,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tear-down of a process group whose collectives were captured in a CUDA graph has been seen to hang in
         # destroy_process_group(); the measurement is complete and printed, so synchronise and leave hard.
@@ -520,6 +529,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) also write to fd 1,
+    # so for the duration of the run fd 1 points at stderr and the JSON line goes to the real stdout at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -56,10 +56,29 @@ def allreduce_sum_(tensors: Sequence[Optional[torch.Tensor]], group=None, big_by
         else:
             small.setdefault((t.dtype, t.device), []).append(t)
     for (_, _), ts in small.items():
-        flat = torch.cat([b.reshape(-1) for b in ts]) if len(ts) > 1 else ts[0].reshape(-1).contiguous()
+        # tensors that are views of ONE storage and cover it densely (the decoder gradients are views of the flat
+        # per-decoder buffers the backward kernel reduced into) are all-reduced as the storage span: no copies
+        by_store = {}
+        for b in ts:
+            by_store.setdefault(b.untyped_storage().data_ptr(), []).append(b)
+        rest = []
+        for _, vs in by_store.items():
+            es = vs[0].element_size()
+            if len(vs) > 1 and all(v.is_contiguous() for v in vs):
+                lo = min(v.storage_offset() for v in vs)
+                hi = max(v.storage_offset() + v.numel() for v in vs)
+                if (hi - lo) <= 2 * sum(v.numel() for v in vs):
+                    span = torch.empty(0, dtype=vs[0].dtype, device=vs[0].device).set_(
+                        vs[0].untyped_storage(), lo, (hi - lo,), (1,))
+                    dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
+                    continue
+            rest.extend(vs)
+        if not rest:
+            continue
+        flat = torch.cat([b.reshape(-1) for b in rest]) if len(rest) > 1 else rest[0].reshape(-1).contiguous()
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         off = 0
-        for b in ts:
+        for b in rest:
             b.copy_(flat[off:off + b.numel()].view_as(b))
             off += b.numel()
 

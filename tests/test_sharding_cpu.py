@@ -30,6 +30,13 @@ def _worker(rank, world, port, q):
         sh.allreduce_sum_([a, None, b, c], big_bytes=64)
         tot = sum(range(1, world + 1))
         assert torch.all(a == tot) and torch.all(b == 10 * tot) and torch.all(c == sum(range(world)))
+        # views of one flat buffer (how decoder gradients arrive) are reduced as one span, in place
+        arena = torch.zeros(40)
+        v1, v2, v3 = arena[4:10].view(2, 3), arena[10:22], arena[22:30].view(4, 2)
+        v1.fill_(float(rank + 1)); v2.fill_(2.0 * (rank + 1)); v3.fill_(3.0 * (rank + 1))
+        sh.allreduce_sum_([v1, v2, v3], big_bytes=1 << 20)
+        assert torch.all(v1 == tot) and torch.all(v2 == 2 * tot) and torch.all(v3 == 3 * tot)
+        assert torch.all(arena[:4] == 0) and torch.all(arena[30:] == 0)
         # ragged all-gather
         rows = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
         counts = [sh.shard_range(11, r, world)[1] - sh.shard_range(11, r, world)[0] for r in range(world)]
