@@ -899,8 +899,9 @@ extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts
                                int apply_bound_mask, float *out4, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
-  if (!pts || !out4 || n < 0) return ENS_EINVAL;
-  if (n == 0) return ENS_OK;
+  if (n < 0) return ENS_EINVAL;
+  if (n == 0) return ENS_OK;                    // empty input: nothing to do (pointers of empty tensors are null)
+  if (!pts || !out4) return ENS_EINVAL;
   const DevScene sc = make_dev_scene(scene);
   cudaStream_t s = (cudaStream_t)stream;
   if (use_mma_forward()) {
@@ -922,7 +923,9 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
                               void *saved, int64_t saved_bytes, int saved_with_activations, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
-  if (!rays_o || !rays_d || !depth || !var || !color || n_rays < 0) return ENS_EINVAL;
+  if (n_rays < 0) return ENS_EINVAL;
+  if (n_rays == 0) return ENS_OK;               // empty batch: a no-op
+  if (!rays_o || !rays_d || !depth || !var || !color) return ENS_EINVAL;
   const bool has_depth = gt_depth != nullptr && stage != ENS_STAGE_COARSE;
   if (has_depth && !depth_max) return ENS_EINVAL;
   int S, ns;
@@ -976,7 +979,9 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
                               int64_t saved_bytes, int saved_with_activations, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
-  if (!rays_o || !rays_d || !raw || !grads || n_rays < 0) return ENS_EINVAL;
+  if (n_rays < 0) return ENS_EINVAL;
+  if (n_rays == 0) return ENS_OK;
+  if (!rays_o || !rays_d || !raw || !grads) return ENS_EINVAL;
   const bool has_depth = gt_depth != nullptr && stage != ENS_STAGE_COARSE;
   if (has_depth && !depth_max) return ENS_EINVAL;
   int S, ns;

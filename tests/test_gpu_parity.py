@@ -203,6 +203,87 @@ def test_render_backward_recompute_path(tiny, stage, use_depth):
                 assert rel_err(p.grad.cpu().numpy(), ref) < TOL_GRAD, (name, key)
 
 
+@pytest.mark.parametrize("n_rays", [1, 5, 13, 37])
+@pytest.mark.parametrize("stage,use_depth", [("color", True), ("fine", False)])
+def test_ragged_ray_counts_vs_oracle(tiny, n_rays, stage, use_depth):
+    """Ray counts that fill neither a forward CTA (8 rays) nor a backward CTA (4 rays) nor a 32-point tile: idle lanes
+    must not contribute, and the forward's saved tiles must line up with the backward's.  Subsets of a kink-safe golden
+    case are kink-safe, so gradients are held to 1e-3 against the oracle run on the same subset."""
+    renderer, decoders, c, g, sc = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"], tiny["sc"]
+    tag = f"{stage}.{'d' if use_depth else 'n'}"
+    for p in decoders.parameters():
+        p.grad = None
+        p.requires_grad_(True)
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    ro_np, rd_np, sd_np = g[f"{tag}.rays_o"][:n_rays], g[f"{tag}.rays_d"][:n_rays], g[f"{tag}.sample_depth"][:n_rays]
+    ro = torch.from_numpy(ro_np.copy()).to(DEV).requires_grad_(True)
+    rd = torch.from_numpy(rd_np.copy()).to(DEV).requires_grad_(True)
+    sd = torch.from_numpy(sd_np.copy()).to(DEV)
+    depth, var, color, raw, z, w = renderer.render_batch_ray_aux(cg, decoders, rd, ro, DEV, stage,
+                                                                gt_depth=sd if use_depth else None)
+    g_d, g_v, g_c = cases.upstream_grads(n_rays)
+    ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+     + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    t32 = torch.linspace(0., 1., 32).numpy()
+    t64 = torch.linspace(0., 1., 16).double().numpy()
+    od, ov, oc, cache = orc.render_batch_ray(sc, ro_np, rd_np, stage, sd_np if use_depth else None, t32, t64)
+    og = orc.render_batch_ray_backward(sc, cache, g_d, g_v, g_c)
+    assert np.array_equal(z.cpu().numpy(), cache["z"])
+    assert rel_err(depth.detach().cpu().numpy(), od) < TOL_OUT and rel_err(var.detach().cpu().numpy(), ov) < TOL_OUT
+    if stage == "color":
+        assert rel_err(color.detach().cpu().numpy(), oc) < TOL_OUT
+    assert rel_err(ro.grad.cpu().numpy(), og["rays_o"]) < TOL_GRAD
+    assert rel_err(rd.grad.cpu().numpy(), og["rays_d"]) < TOL_GRAD
+    for name in orc.STAGE_DECODERS[stage]:
+        gk = "grid_" + name
+        assert rel_err(cg[gk].grad.cpu().numpy(), og["grids"][gk]) < TOL_GRAD, gk
+        for key, p in getattr(decoders, name + "_decoder").named_parameters():
+            ref = og["decoders"][name][key]
+            if np.abs(ref).max() > 0:
+                assert rel_err(p.grad.cpu().numpy(), ref) < TOL_GRAD, (name, key)
+
+
+def test_empty_batch_is_a_no_op(tiny):
+    renderer, decoders, c = tiny["renderer"], tiny["decoders"], tiny["c"]
+    ro = torch.empty(0, 3, device=DEV); rd = torch.empty(0, 3, device=DEV); sd = torch.empty(0, device=DEV)
+    d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=None)
+    assert d.shape == (0,) and u.shape == (0,) and col.shape == (0, 3)
+    out = renderer.eval_points(torch.empty(0, 3, device=DEV, dtype=torch.float64), decoders, c, "fine", DEV)
+    assert out.shape == (0, 4)
+
+
+def test_forward_is_independent_of_batch_boundaries():
+    """Size-independent property at full scale (room0, 20 000 rays): one call equals the concatenation of ragged
+    chunks BIT FOR BIT when the chunks are given the whole batch's depth maxima (what sharding.py passes), and
+    eval_points of 300 000 lattice points equals its chunked evaluation."""
+    from evennicer_slam_b200 import harness, functional, common
+    scene = cases.room0_scene()
+    decoders, c, renderer, cfg = harness.build(scene, DEV, requires_grad=False)
+    cam_t, depth, color, event = cases.room0_frame()
+    cam = scene.cam
+    torch.manual_seed(3)
+    c2w = common.get_camera_from_tensor(torch.from_numpy(cam_t.copy()).to(DEV))
+    ro, rd, sd, _ = common.get_samples(0, cam.H, 0, cam.W, 20000, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w,
+                                       torch.from_numpy(depth).to(DEV), torch.from_numpy(color).to(DEV), DEV)
+    setup = renderer._setup("color", decoders, DEV)
+    dmax = functional.depth_batch_max(sd.contiguous())
+    full = functional.render_batch_ray(setup, c, decoders, rd, ro, sd, depth_max=dmax)
+    parts = []
+    for lo, hi in ((0, 1), (1, 4098), (4098, 4099), (4099, 20000)):
+        parts.append(functional.render_batch_ray(setup, c, decoders, rd[lo:hi], ro[lo:hi], sd[lo:hi], depth_max=dmax))
+    for k in range(3):
+        assert torch.equal(full[k], torch.cat([p[k] for p in parts])), k
+    assert torch.isfinite(full[0]).all() and torch.isfinite(full[2]).all()
+    b = scene.bound
+    pts = torch.rand(300000, 3, device=DEV, dtype=torch.float64) * torch.tensor(b[:, 1] - b[:, 0] + 0.4, device=DEV) \
+        + torch.tensor(b[:, 0] - 0.2, device=DEV)
+    whole = renderer.eval_points(pts, decoders, c, "color", DEV)
+    chunks = torch.cat([renderer.eval_points(pts[a:e], decoders, c, "color", DEV)
+                        for a, e in ((0, 7), (7, 100001), (100001, 300000))])
+    assert torch.equal(whole, chunks)
+    assert int((whole[:, 3] == 100).sum()) > 0 and int((whole[:, 3] != 100).sum()) > 0
+
+
 def test_backward_without_decoder_or_grid_grads_matches(tiny):
     """Tracker-style call: only the rays need gradient (decoder/grid grads skipped in the kernel)."""
     g = tiny["g"]
