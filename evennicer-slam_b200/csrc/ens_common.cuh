@@ -152,16 +152,42 @@ struct CoarseGrad {
   __host__ __device__ static constexpr int total() { return off_bo() + 1; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Packed decoder blob, "tc" layout (tcgen05 / UMMA forward).  Every [32][K] matrix is stored in the canonical
+// K-major, no-swizzle UMMA shared-memory layout (8-row x 16-byte core matrices):
+//     element (n, k) at  (n/8)*(K/4)*32 + (k/4)*32 + (n%8)*4 + (k%4)   floats      (SBO = (K/4)*128 B, LBO = 128 B)
+// twice: the value itself (the tensor core reads its top 19 bits = the TF32 "hi" part) and, TOT floats further,
+// the remainder  lo = w - tf32_trunc(w)  for the 3xTF32 passes.
+//   matrices, in order: W0 [32][96], W3e [32][96], Wh_1, Wh_2, Wh_3 (hidden part), Wh_4 [32][32], Wc_0..Wc_4 [32][CD]
+//   then: B [3][96], b_i [5][32], bc_i [5][32], Wo [4][32] (rows >= NO zero), bo [4]
+// ---------------------------------------------------------------------------------------------
+template <int CD>
+struct MlpPackTC {
+  __host__ __device__ static constexpr int off_W0() { return 0; }
+  __host__ __device__ static constexpr int off_W3e() { return 32 * EMBP; }
+  __host__ __device__ static constexpr int off_Wh(int i) { return 2 * 32 * EMBP + (i - 1) * 1024; }   // i = 1..4
+  __host__ __device__ static constexpr int off_Wc(int i) { return 2 * 32 * EMBP + 4 * 1024 + i * 32 * CD; }
+  __host__ __device__ static constexpr int TOT() { return 2 * 32 * EMBP + 4 * 1024 + 5 * 32 * CD; }
+  __host__ __device__ static constexpr int off_B() { return 2 * TOT(); }
+  __host__ __device__ static constexpr int off_b(int i) { return off_B() + 3 * EMBP + 32 * i; }
+  __host__ __device__ static constexpr int off_bc(int i) { return off_B() + 3 * EMBP + 160 + 32 * i; }
+  __host__ __device__ static constexpr int off_Wo() { return off_B() + 3 * EMBP + 320; }
+  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int total() { return off_bo() + 4; }
+};
+__host__ __device__ constexpr int canon_off(int n, int k, int K) { return (n / 8) * (K / 4) * 32 + (k / 4) * 32 + (n % 8) * 4 + (k % 4); }
+
 // A packed blob holds the fma layout, the mma forward layout and the mma backward layout (coarse: fma only).
 __host__ __device__ inline int packed_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarsePack::total();
-    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total() + MlpPackV2B::total();
-    default: return MlpPack<32>::total() + MlpPackV2<32>::total() + MlpPackV2B::total();
+    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total() + MlpPackV2B::total() + MlpPackTC<64>::total();
+    default: return MlpPack<32>::total() + MlpPackV2<32>::total() + MlpPackV2B::total() + MlpPackTC<32>::total();
   }
 }
 template <int CD> __host__ __device__ constexpr int off_v2() { return MlpPack<CD>::total(); }
 template <int CD> __host__ __device__ constexpr int off_v2b() { return MlpPack<CD>::total() + MlpPackV2<CD>::total(); }
+template <int CD> __host__ __device__ constexpr int off_tc() { return off_v2b<CD>() + MlpPackV2B::total(); }
 __host__ __device__ inline int grad_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarseGrad::total();

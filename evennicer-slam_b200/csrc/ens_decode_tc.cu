@@ -1,0 +1,323 @@
+// NICE.forward on the 5th-generation tensor cores (tcgen05 / UMMA, accumulators in TMEM) -- variant "tc".
+//
+// One launch decodes ONE decoder (middle, fine or colour) for N points; the stage dispatch of NICE.forward
+// (decoder.py:312-342) is a sequence of launches that read-modify-write the (N,4) output:
+//     middle: out = (0,0,0,occ_m)      fine: out.w = occ_f + out.w      colour: out.xyz = rgb
+// and the last launch applies Renderer.eval_points' bound rule (out.w = 100 outside slam.bound, Renderer.py:43-58).
+//
+// Mapping.  A persistent CTA (one per SM) stages the decoder's weights once -- every [32][K] matrix twice, as the
+// value and as its TF32 remainder, in the canonical K-major UMMA layout (MlpPackTC) -- and then walks 128-point tiles.
+// Thread r of the CTA owns point r of the tile = TMEM lane r (thread-per-point epilogue):
+//   * trilinear gather of its 32 (64) features, split hi/lo, tcgen05.st into the feature columns (A operand in TMEM);
+//   * Fourier embedding in three 32-column chunks: sin -> hi/lo -> tcgen05.st; one elected thread issues
+//     D  += e W0^T  and  D3 += e W3e^T  (3xTF32: lo.hi, hi.lo, hi.hi; M = 128 points, N = 32, K = 8 per instruction);
+//   * per block i: tcgen05.ld of D (W_i x) and Dc (Wc_i c); h = relu(D + b_i) + Dc + bc_i in registers; hi/lo -> x
+//     columns; next block's hidden GEMM (into D, or into D3 for the skip block) and feature GEMM are issued;
+//   * output layer on the FMA pipe (32 x NO), read-modify-write of the output row.
+// Completion of each MMA batch is tracked with tcgen05.commit -> mbarrier; thread sync around TMEM stores uses
+// tcgen05.wait::st + tcgen05.fence + bar.sync.  Verified first in isolation by scratch/tc_probe.cu.
+#include "ens_mma.cuh"
+
+namespace ens {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: LBO = 128 B between the two K core matrices, SBO = (K/4)*128 B between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((128u >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell)
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, N = 32, K = 8
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "TC_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE_%=;\n\t"
+      "bra TC_WAIT_%=;\n\t"
+      "TC_DONE_%=:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+               "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// store 32 values as the A operand: the value itself (hi: the tensor core reads its top 19 bits) at `thi`, the TF32
+// remainder at `tlo`
+__device__ __forceinline__ void tmem_st32_split(uint32_t thi, uint32_t tlo, const float (&v)[32]) {
+  uint32_t h[32], l[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    h[i] = __float_as_uint(v[i]);
+    l[i] = __float_as_uint(v[i] - __uint_as_float(h[i] & 0xffffe000u));
+  }
+#define ENS_ST32(addr, r)                                                                                      \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                 \
+               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "  \
+               "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"                                \
+               :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), \
+                 "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), \
+                 "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) \
+               : "memory")
+  ENS_ST32(thi, h);
+  ENS_ST32(tlo, l);
+#undef ENS_ST32
+}
+__device__ __forceinline__ void tmem_st_done() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// trilinear feature of one point into registers (same corner order / fma order as gather32 and gather_warp)
+__device__ __forceinline__ void gather_regs(const float *__restrict__ grid, const int dims[3], const float pn[3],
+                                            float (&f)[32]) {
+  const Vox v = make_vox(pn, dims);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    int64_t lin; float w;
+    corner(v, dims, c, lin, w);
+    const float4 *src = reinterpret_cast<const float4 *>(grid + lin);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = __ldg(src + q);
+      f[4 * q + 0] = fmaf(a.x, w, f[4 * q + 0]); f[4 * q + 1] = fmaf(a.y, w, f[4 * q + 1]);
+      f[4 * q + 2] = fmaf(a.z, w, f[4 * q + 2]); f[4 * q + 3] = fmaf(a.w, w, f[4 * q + 3]);
+    }
+  }
+}
+
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// issue  D (+)= A[128 x K] * W[32 x K]^T  in 3xTF32; A: hi at a_hi, lo at a_lo (TMEM columns), W: canonical smem
+// matrix at float offset w_off (value) and w_off + TOT (remainder).  first_acc: 0 = overwrite D with the first MMA.
+template <int K, int KMAT>
+__device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t sw_base, int w_off, int tot,
+                                           uint32_t first_acc) {
+  // K columns of a [32][KMAT] canonical matrix starting at float offset w_off (a column offset of 4c inside the
+  // matrix is c*128 bytes and is folded into sw_base by the caller); SBO is that of the WHOLE matrix
+  const uint64_t dh = umma_desc(sw_base + (uint32_t)w_off * 4u, (KMAT / 4) * 128u);
+  const uint64_t dl = umma_desc(sw_base + (uint32_t)(w_off + tot) * 4u, (KMAT / 4) * 128u);
+  uint32_t acc = first_acc;
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) { umma_ts(d, a_lo + 8 * ks, dh + (uint64_t)(16 * ks), TC_IDESC, acc); acc = 1; }
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dl + (uint64_t)(16 * ks), TC_IDESC, 1);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dh + (uint64_t)(16 * ks), TC_IDESC, 1);
+}
+
+struct TcArgs {
+  DevScene sc;
+  const void *pts;        // [n][3] f64 or f32
+  int64_t n;
+  float *out4;            // [n][4]
+  int apply_mask;         // last launch of the stage and the caller wants the bound rule
+};
+
+// TMEM columns (one 128-point tile in flight)
+constexpr int TC_D = 0, TC_D3 = 32, TC_DC = 64, TC_EH = 96, TC_EL = 128, TC_XH = 160, TC_XL = 192, TC_FH = 224, TC_FL = 288;
+constexpr int TC_COLS = 512;
+
+template <int LEVEL, int CD, int NO, bool F64>
+__global__ void __launch_bounds__(128, 1) decode_tc_kernel(TcArgs a) {
+  using P = MlpPackTC<CD>;
+  extern __shared__ __align__(128) float smem[];
+  float *sw = smem;                                     // the tc blob
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  {   // stage the blob once per CTA
+    const float *gw = a.sc.w[LEVEL] + off_tc<CD>();
+    const uint32_t s0 = smem_u32(sw);
+    for (int i = tid; i < P::total() / 4; i += 128)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TC_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged weights -> visible to the UMMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s + ((uint32_t)(32 * warp) << 16);      // this warp's lane quarter
+  const uint32_t tb0 = tmem_base_s;                                     // MMA operands address lane 0
+  const uint32_t swb = smem_u32(sw);
+  uint32_t parity = 0;
+
+  const int64_t n_tiles = (a.n + 127) / 128;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t pt = tile * 128 + tid;
+    const bool valid = pt < a.n;
+    float pn[3], p32[3];
+    bool inside = true;
+    if (F64) {
+      double p[3] = {0.0, 0.0, 0.0};
+      if (valid) { const double *pp = (const double *)a.pts + pt * 3; p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2]; }
+      normalize64(p, a.sc.lo, a.sc.hi, pn);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { p32[k] = __double2float_rn(p[k]); inside &= (p[k] < a.sc.hi[k]) && (p[k] > a.sc.lo[k]); }
+    } else {
+      if (valid) { const float *pp = (const float *)a.pts + pt * 3; p32[0] = pp[0]; p32[1] = pp[1]; p32[2] = pp[2]; }
+      else { p32[0] = p32[1] = p32[2] = 0.f; }
+      normalize32(p32, a.sc.lo, a.sc.hi, pn);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        inside &= (p32[k] < __double2float_rn(a.sc.hi[k])) && (p32[k] > __double2float_rn(a.sc.lo[k]));
+    }
+
+    // ---- features -> TMEM (A operand of the five fc_c GEMMs) ----
+    {
+      float f[32];
+      gather_regs(a.sc.grid[LEVEL], a.sc.dims[LEVEL], pn, f);
+      tmem_st32_split(tb + TC_FH, tb + TC_FL, f);
+      if (CD == 64) {      // fine decoder: [fine | middle] concat (decoder.py:182-187)
+        gather_regs(a.sc.grid[ENS_LEVEL_MIDDLE], a.sc.dims[ENS_LEVEL_MIDDLE], pn, f);
+        tmem_st32_split(tb + TC_FH + 32, tb + TC_FL + 32, f);
+      }
+    }
+    // ---- embedding chunks: D += e W0^T, D3 += e W3e^T ----
+#pragma unroll 1
+    for (int jc = 0; jc < 3; ++jc) {
+      float e[32];
+      const float *B = sw + P::off_B() + 32 * jc;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float q = fmaf(p32[2], B[2 * EMBP + k], fmaf(p32[1], B[EMBP + k], p32[0] * B[k]));
+        e[k] = fast_sin(q);
+      }
+      if (jc > 0) { mbar_wait(&bar, parity); parity ^= 1; tc_fence_after(); }     // previous chunk consumed
+      tmem_st32_split(tb + TC_EH, tb + TC_EL, e);
+      tmem_st_done();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        // chunk jc = columns 32jc..32jc+31 of the [32][96] matrices = k-steps 4jc..4jc+3: +8 core matrices = +1024 B
+        issue_gemm<32, EMBP>(tb0 + TC_D, tb0 + TC_EH, tb0 + TC_EL, swb + jc * 1024, P::off_W0(), P::TOT(), jc > 0);
+        issue_gemm<32, EMBP>(tb0 + TC_D3, tb0 + TC_EH, tb0 + TC_EL, swb + jc * 1024, P::off_W3e(), P::TOT(), jc > 0);
+        if (jc == 2) issue_gemm<CD, CD>(tb0 + TC_DC, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_Wc(0), P::TOT(), 0);   // Wc_0 c
+        umma_commit(&bar);
+      }
+    }
+    // ---- blocks 0..4 ----
+    float h[32];
+#pragma unroll 1
+    for (int i = 0; i < 5; ++i) {
+      mbar_wait(&bar, parity); parity ^= 1;
+      tc_fence_after();
+      float u[32], c[32];
+      tmem_ld32(tb + (i == 3 ? TC_D3 : TC_D), u);
+      tmem_ld32(tb + TC_DC, c);
+      const float *bi = sw + P::off_b(0) + 32 * i, *bci = sw + P::off_bc(0) + 32 * i;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) h[k] = fmaxf(u[k] + bi[k], 0.f) + (c[k] + bci[k]);
+      if (i < 4) {
+        tmem_st32_split(tb + TC_XH, tb + TC_XL, h);
+        tmem_st_done();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          // next block's hidden GEMM: into D3 (which already holds W3e e) for the skip block, else overwrite D
+          if (i + 1 == 3) issue_gemm<32, 32>(tb0 + TC_D3, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(3), P::TOT(), 1);
+          else issue_gemm<32, 32>(tb0 + TC_D, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(1) + i * 1024, P::TOT(), 0);
+          issue_gemm<CD, CD>(tb0 + TC_DC, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_Wc(0) + (i + 1) * 32 * CD, P::TOT(), 0);
+          umma_commit(&bar);
+        }
+      }
+    }
+    // ---- output layer (FMA pipe), read-modify-write of the output row ----
+    float o[NO];
+#pragma unroll
+    for (int q = 0; q < NO; ++q) {
+      const float *Wo = sw + P::off_Wo() + 32 * q;
+      float s = sw[P::off_bo() + q];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) s = fmaf(Wo[k], h[k], s);
+      o[q] = s;
+    }
+    if (valid) {
+      float4 *dst = reinterpret_cast<float4 *>(a.out4) + pt;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LEVEL == ENS_LEVEL_MIDDLE) r.w = o[0];
+      else if (LEVEL == ENS_LEVEL_FINE) { r = *dst; r.w = __fadd_rn(o[0], r.w); }
+      else { r = *dst; r.x = o[0]; r.y = o[1]; r.z = o[2]; }
+      if (a.apply_mask && !inside) r.w = 100.f;
+      *dst = r;
+    }
+    // the next tile's first tcgen05.st must not overtake this tile's TMEM loads
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"((uint32_t)TC_COLS) : "memory");
+}
+
+template <int LEVEL, int CD, int NO>
+static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s) {
+  TcArgs a;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask;
+  const size_t smem = (size_t)MlpPackTC<CD>::total() * 4;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (n + 127) / 128;
+  const unsigned g = (unsigned)(tiles < sms ? tiles : sms);
+  if (f64) {
+    if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    decode_tc_kernel<LEVEL, CD, NO, true><<<g, 128, smem, s>>>(a);
+  } else {
+    if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    decode_tc_kernel<LEVEL, CD, NO, false><<<g, 128, smem, s>>>(a);
+  }
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+// NICE.forward / Renderer.eval_points for stages middle, fine, color: one launch per decoder of the stage.
+int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
+                   float *out4, cudaStream_t s) {
+  if (stage == ENS_STAGE_COARSE) return ENS_EUNSUPPORTED;
+  int rc = launch_decode_tc<ENS_LEVEL_MIDDLE, 32, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_MIDDLE ? apply_mask : 0, out4, s);
+  if (rc != ENS_OK || stage == ENS_STAGE_MIDDLE) return rc;
+  rc = launch_decode_tc<ENS_LEVEL_FINE, 64, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_FINE ? apply_mask : 0, out4, s);
+  if (rc != ENS_OK || stage == ENS_STAGE_FINE) return rc;
+  return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s);
+}
+
+}  // namespace ens

@@ -167,7 +167,42 @@ __device__ __forceinline__ void pack_mlp_v2b_body(const PtrTable &t, float *__re
   out[idx] = v;
 }
 
-// one launch packs all three sections of a decoder blob (fma | mma forward | mma backward)
+// tcgen05 layout (see MlpPackTC): canonical UMMA K-major core matrices, value and tf32 remainder
+template <int CD, int NO>
+__device__ __forceinline__ void pack_mlp_tc_body(const PtrTable &t, float *__restrict__ out, int idx) {
+  using P = MlpPackTC<CD>;
+  float v = 0.f;
+  if (idx < 2 * P::TOT()) {
+    const bool lo = idx >= P::TOT();
+    int o = lo ? idx - P::TOT() : idx;
+    // which matrix
+    int K, mat, i = 0;
+    if (o < P::off_W3e()) { mat = 0; K = EMBP; }
+    else if (o < P::off_Wh(1)) { mat = 1; K = EMBP; o -= P::off_W3e(); }
+    else if (o < P::off_Wc(0)) { mat = 2; K = 32; o -= P::off_Wh(1); i = 1 + o / 1024; o %= 1024; }
+    else { mat = 3; K = CD; o -= P::off_Wc(0); i = o / (32 * CD); o %= (32 * CD); }
+    const int ni = o / ((K / 4) * 32), r1 = o % ((K / 4) * 32);
+    const int ki = r1 / 32, r2 = r1 % 32;
+    const int n = ni * 8 + r2 / 4, k = ki * 4 + r2 % 4;
+    float w = 0.f;
+    if (mat == 0) w = (k < EMB) ? t.p[11][n * EMB + k] : 0.f;
+    else if (mat == 1) w = (k < EMB) ? t.p[11 + 2 * 3][n * 125 + k] : 0.f;
+    else if (mat == 2) w = (i == 3) ? t.p[11 + 2 * 3][n * 125 + EMB + k] : t.p[11 + 2 * i][n * 32 + k];
+    else w = t.p[2 * i][n * CD + k];
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    v = lo ? (w - hi) : w;
+  } else {
+    int o = idx - P::off_B();
+    if (o < 3 * EMBP) { int r = o / EMBP, k = o % EMBP; v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f; }
+    else if (o < 3 * EMBP + 160) { o -= 3 * EMBP; v = t.p[12 + 2 * (o / 32)][o % 32]; }
+    else if (o < 3 * EMBP + 320) { o -= 3 * EMBP + 160; v = t.p[2 * (o / 32) + 1][o % 32]; }
+    else if (o < 3 * EMBP + 320 + 128) { o -= 3 * EMBP + 320; int n = o / 32, j = o % 32; v = (n < NO) ? t.p[21][n * 32 + j] : 0.f; }
+    else { int n = o - (3 * EMBP + 320 + 128); v = (n < NO) ? t.p[22][n] : 0.f; }
+  }
+  out[idx] = v;
+}
+
+// one launch packs all sections of a decoder blob (fma | mma forward | mma backward | tcgen05)
 template <int CD, int NO>
 __global__ void pack_mlp_all_kernel(PtrTable t, float *__restrict__ out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,7 +210,9 @@ __global__ void pack_mlp_all_kernel(PtrTable t, float *__restrict__ out) {
   idx -= MlpPack<CD>::total();
   if (idx < MlpPackV2<CD>::total()) { pack_mlp_v2_body<CD, NO>(t, out + off_v2<CD>(), idx); return; }
   idx -= MlpPackV2<CD>::total();
-  if (idx < MlpPackV2B::total()) pack_mlp_v2b_body<CD, NO>(t, out + off_v2b<CD>(), idx);
+  if (idx < MlpPackV2B::total()) { pack_mlp_v2b_body<CD, NO>(t, out + off_v2b<CD>(), idx); return; }
+  idx -= MlpPackV2B::total();
+  if (idx < MlpPackTC<CD>::total()) pack_mlp_tc_body<CD, NO>(t, out + off_tc<CD>(), idx);
 }
 
 __global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {

@@ -904,6 +904,13 @@ extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts
   if (!pts || !out4) return ENS_EINVAL;
   const DevScene sc = make_dev_scene(scene);
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    const char *v = std::getenv("ENS_EVAL_VARIANT");          // "tc" (tcgen05) | "mma" | "fma"
+    if (v && std::strcmp(v, "tc") == 0) {
+      rc = tc_eval_points(sc, stage, pts, pts_is_f64, n, apply_bound_mask, out4, s);
+      if (rc != ENS_EUNSUPPORTED) return rc;
+    }
+  }
   if (use_mma_forward()) {
     rc = mma_eval_points(sc, stage, pts, pts_is_f64, n, apply_bound_mask, out4, s);
     if (rc != ENS_EUNSUPPORTED) return rc;       // coarse stage: fma kernels below

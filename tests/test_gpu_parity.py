@@ -35,7 +35,7 @@ def test_library_loads_and_reports_version():
     from evennicer_slam_b200 import _lib
     L = _lib.lib()
     assert L.ens_version() == 2
-    assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 and L.ens_decoder_grad_floats(3) == 15899
+    assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 + 41700 and L.ens_decoder_grad_floats(3) == 15899
 
 
 def test_grid_layout_roundtrip():
@@ -120,6 +120,24 @@ def test_eval_points(tiny, stage):
     bare = decoders(torch.from_numpy(pts).to(DEV)[None], c_grid=c, stage=stage).cpu().numpy()
     inside = ref[:, 3] != 100
     assert rel_err(bare[inside], ref[inside]) < TOL_OUT and not np.any(bare[:, 3] == 100)
+
+
+@pytest.mark.parametrize("stage", ["middle", "fine", "color"])
+def test_eval_points_tcgen05_variant(tiny, stage, monkeypatch):
+    """The tcgen05/TMEM decode (ens_decode_tc.cu; opt-in with ENS_EVAL_VARIANT=tc) against the reference goldens."""
+    monkeypatch.setenv("ENS_EVAL_VARIANT", "tc")
+    scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
+    g = load_golden("tiny_eval_points.npz")
+    pts = cases.eval_points_lattice(scene)
+    for dt, key in ((np.float64, "f64"), (np.float32, "f32")):
+        out = renderer.eval_points(torch.from_numpy(pts.astype(dt)).to(DEV), decoders, c, stage, DEV).cpu().numpy()
+        ref = g[f"{stage}.{key}"]
+        assert np.array_equal(out[:, 3] == 100, ref[:, 3] == 100)
+        assert rel_err(out, ref) < TOL_OUT
+    # ragged sizes: not a multiple of the 128-point tile, fewer tiles than SMs, one point
+    for n in (1, 127, 129, 300):
+        out = renderer.eval_points(torch.from_numpy(pts[:n]).to(DEV), decoders, c, stage, DEV).cpu().numpy()
+        assert rel_err(out, g[f"{stage}.f64"][:n]) < TOL_OUT
 
 
 def _run_case(tiny, stage, use_depth, with_params=True):
