@@ -355,6 +355,7 @@ def run_gpu_arm(args):
 
     # ---- tracking iteration (config C2), reported beside the headline ----
     track_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
+    other = measure_other_configs(dev, renderer, decoders, c, frames, scene) if (rank == 0 and not args.no_other_configs) else None
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -376,7 +377,7 @@ def run_gpu_arm(args):
             "config": workload_config(), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_timed, "gpu_launches_per_step": launches_timed / args.steps,
             "roofline": roof, "cpu_baseline": cpu,
-            "tracking_ms_per_iter": track_ms, "wall_s_timed_region": t_wall,
+            "tracking_ms_per_iter": track_ms, "other_configs": other, "wall_s_timed_region": t_wall,
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": eager_ms,
         }
@@ -520,6 +521,74 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
     return tot / iters
 
 
+def measure_other_configs(dev, renderer, decoders, c, frames, scene):
+    """Reported beside the headline (BASELINE.json configs 2, 4, 5): CUDA-event times, inputs resident.
+
+      event_render   : Tracker.py:150 -- render_img_rescale(0.15) = 102 x 180 = 18 360 rays, colour stage, forward +
+                       backward into the camera tensor only
+      full_frame     : Renderer.render_img, 680 x 1200 = 816 000 rays in the reference's 100 000-ray batches, no grad
+      mesh_lattice   : eval_points('fine') over 256^3 = 16 777 216 lattice points in 500 000-point chunks (Mesher.py)
+    """
+    import torch
+    from evennicer_slam_b200 import common
+    cam = scene.cam
+    cam_t, depth, color = frames[-1]
+    depth_t = torch.from_numpy(depth).to(dev)
+    req = [p.requires_grad for p in decoders.parameters()]
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+    out = {}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ct = torch.from_numpy(cam_t.copy()).to(dev).requires_grad_(True)
+
+    def event_render():
+        ct.grad = None
+        c2w = common.get_camera_from_tensor(ct)
+        d, u, col = renderer.render_img_rescale(c, decoders, c2w, dev, "color", gt_depth=depth_t, scale_factor=0.15)
+        (col.sum() + d.sum()).backward()
+    ms = timed(event_render, 5)
+    n = int(cam.H * 0.15) * int(cam.W * 0.15)
+    out["event_render"] = {"rays": n, "ms": ms, "rays_per_s": n / ms * 1e3,
+                           "frac_of_hbm_roofline": n / ms * 1e3 * 294912 / (hbm_peak()[0] * 1e9)}
+
+    c2w = common.get_camera_from_tensor(ct).detach()
+
+    def full_frame():
+        renderer.render_img(c, decoders, c2w, dev, "color", gt_depth=depth_t)
+    ms = timed(full_frame, 2)
+    n = cam.H * cam.W
+    out["full_frame"] = {"rays": n, "ms": ms, "rays_per_s": n / ms * 1e3,
+                         "frac_of_hbm_roofline": n / ms * 1e3 * 147456 / (hbm_peak()[0] * 1e9)}
+
+    b = scene.bound
+    lin = [torch.linspace(float(b[k, 0]), float(b[k, 1]), 256, device=dev, dtype=torch.float64) for k in range(3)]
+    chunk = 500000
+
+    def mesh():
+        # the 256^3 lattice of Mesher.get_grid_uniform, generated chunk by chunk (x fastest, as np.meshgrid ravel)
+        total = 256 ** 3
+        for lo in range(0, total, chunk * 8):
+            idx = torch.arange(lo, min(total, lo + chunk * 8), device=dev)
+            pts = torch.stack([lin[0][idx % 256], lin[1][(idx // 256) % 256], lin[2][idx // 65536]], -1)
+            renderer.eval_points(pts, decoders, c, "fine", dev)
+    ms = timed(mesh, 1)
+    n = 256 ** 3
+    out["mesh_lattice"] = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3,
+                           "frac_of_hbm_roofline": n / ms * 1e3 * 2048 / (hbm_peak()[0] * 1e9)}
+    for p, r in zip(decoders.parameters(), req):
+        p.requires_grad_(r)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -528,6 +597,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the event-render / full-frame / mesh timings")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) also write to fd 1,
     # so for the duration of the run fd 1 points at stderr and the JSON line goes to the real stdout at the end.

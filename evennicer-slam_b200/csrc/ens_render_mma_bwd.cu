@@ -180,7 +180,12 @@ template <int STAGE, bool WG, bool RECOMP>
 struct BwdCfg {
   static constexpr int NT = (WG || !RECOMP) ? 192 : 256;
   static constexpr int NW = NT / 32;
-  static constexpr int RS = MmaStage<STAGE>::RS;
+  // feature tile row length: 64 when a fine decoder needs [fine | middle] features; the pose-only saved-forward
+  // variant never gathers features (the tile is only the staging area of the trilinear backward): 32
+  static constexpr int RS = (WG || RECOMP) ? MmaStage<STAGE>::RS : 32;
+  // that variant (tracking, event render: thousands of rays) is tuned for throughput: 102 KB of shared memory and
+  // <= 168 registers, so two CTAs (12 warps) share an SM
+  static constexpr int MIN_CTAS = (WG || RECOMP) ? 1 : 2;
   static constexpr int WREG = RECOMP ? MmaStage<STAGE>::WMAX : MlpPackV2B::total();   // forward blob >= backward blob
   static constexpr int TILE = NT * 32;                                  // floats of one staging tile
   static constexpr int NTILES = WG ? 3 : 0;                             // sG, sG2, sX
@@ -549,7 +554,8 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int STAGE, bool WG, bool RECOMP>
-__global__ void __launch_bounds__(BwdCfg<STAGE, WG, RECOMP>::NT, 1) render_bwd_mma_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(BwdCfg<STAGE, WG, RECOMP>::NT, BwdCfg<STAGE, WG, RECOMP>::MIN_CTAS)
+render_bwd_mma_kernel(BwdArgs a) {
   using CFG = BwdCfg<STAGE, WG, RECOMP>;
   constexpr int NT = CFG::NT;
   constexpr int RS = CFG::RS;
