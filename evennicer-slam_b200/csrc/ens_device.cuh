@@ -221,6 +221,10 @@ struct BwdArgs {
   float *gdec[4];
   float *g_rays_o, *g_rays_d;
   float *hscratch;          // activation scratch when decoder grads are requested (ens_bwd_workspace_bytes)
+  // split mapping backward: scratch between the data-gradient kernel and the weight-gradient kernel
+  float *split_gh;          // [3 decoders][n_tiles][5][1024]  g_h tiles
+  uint32_t *split_mw;       // [3 decoders][n_tiles][5][32]    relu mask words per point
+  float *split_pts;         // [n_tiles][32][8]                p.float(), valid, normalised coordinates
 };
 
 constexpr int NT_RENDER = 192;   // fma variant: 4 rays x 48 samples (6 x 32-sample rays)

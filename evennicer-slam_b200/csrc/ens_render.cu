@@ -1029,6 +1029,8 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   if (wg && !saved_covers) {
     if (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1)) return ENS_ESHAPE;
   }
+  // with saved activations the workspace is optional: given (and large enough) it enables the split backward
+  if (wg && saved_covers && (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1))) a.hscratch = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   if (use_mma_backward()) {
     rc = mma_render_bwd(a, stage, wg, s);

@@ -176,7 +176,10 @@ __device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, 
 // ---------------------------------------------------------------------------------------------
 // RECOMP = true: the forward saved nothing usable, recompute it here (steps 1-2 above).  RECOMP = false: relu masks
 // (and, for WG, the activation tiles h_0..h_4) come from the buffer the forward kernel wrote.
-template <int STAGE, bool WG, bool RECOMP>
+// SPLIT = true (with WG = false, RECOMP = false): the "split" mapping backward.  This kernel does everything but the
+// weight-gradient GEMMs -- it has the 2-CTA/SM footprint of the pose-only variant -- and writes the five g_h tiles,
+// per-point relu mask words and the points to a scratch; wgrad_split_kernel (below) turns them into decoder gradients.
+template <int STAGE, bool WG, bool RECOMP, bool SPLIT = false>
 struct BwdCfg {
   static constexpr int NT = (WG || !RECOMP) ? 192 : 256;
   static constexpr int NW = NT / 32;
@@ -217,11 +220,11 @@ struct WarpCtx {
 //   p32        : owner lane's p.float();  pn: its normalised coordinates
 //   gp         : owner lane's accumulated d L / d p (float64)
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG, bool RECOMP, int LEVEL, int CD, int NO>
+template <int STAGE, bool WG, bool RECOMP, bool SPLIT, int LEVEL, int CD, int NO>
 __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restrict__ sw, const WarpCtx &w,
                                                 const float pn[3], const float p32[3], const float (&gout)[NO],
                                                 bool valid, bool want_rays, double gp[3]) {
-  using CFG = BwdCfg<STAGE, WG, RECOMP>;
+  using CFG = BwdCfg<STAGE, WG, RECOMP, SPLIT>;
   constexpr int RS = CFG::RS;
   constexpr int NT = CFG::NT;
   constexpr int DEC = (LEVEL == ENS_LEVEL_MIDDLE) ? 0 : (LEVEL == ENS_LEVEL_FINE ? 1 : 2);
@@ -232,11 +235,11 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   const int lane = w.lane, g = w.g, t = w.t;
   float *gdec = a.gdec[LEVEL];
   float *ggrid = a.ggrid[LEVEL];
-  const bool need_emb = WG || want_rays;
+  const bool need_emb = WG || SPLIT || want_rays;
 
   // ---- 1. stage the weights (RECOMP: forward blob; otherwise directly the transposed blob), gather features ----
   // activation tiles h_0..h_4 of this warp: own scratch when recomputed, else what the forward saved
-  const float *hsrc = RECOMP ? w.hs : (WG ? a.save_h + ((int64_t)DEC * a.n_tiles + w.gtile) * 5120 : nullptr);
+  const float *hsrc = RECOMP ? w.hs : ((WG || SPLIT) ? a.save_h + ((int64_t)DEC * a.n_tiles + w.gtile) * 5120 : nullptr);
   __syncthreads();
   if (RECOMP) stage_blob(sw, a.sc.w[LEVEL] + off_v2<CD>(), PF::total());
   else stage_blob(sw, a.sc.w[LEVEL] + off_v2b<CD>(), PB::total());
@@ -305,7 +308,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
       const uint32_t *ms = a.save_masks + (((int64_t)DEC * a.n_tiles + w.gtile) * 5) * 32 + lane;
 #pragma unroll
       for (int k = 0; k < 5; ++k) mask[k] = ms[k * 32];
-      if (WG) load_tile<32>(hsrc + 4 * 1024, 0, acc, g, t);                 // h_4 for dWo
+      if (WG || SPLIT) load_tile<32>(hsrc + 4 * 1024, 0, acc, g, t);        // h_4 for dWo
     }
     // decoder-output gradients of my four rows
     float gr[4][NO];
@@ -313,7 +316,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int o = 0; o < NO; ++o) gr[j][o] = __shfl_sync(0xffffffffu, gout[o], g + 8 * j);
-    if (WG) {
+    if (WG || SPLIT) {
       // dWo[o][n] = sum_pt gout[pt][o] h4[pt][n]; dbo[o] = sum_pt gout[pt][o]
 #pragma unroll
       for (int o = 0; o < NO; ++o) {
@@ -380,6 +383,25 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
     if (WG) {
       store_tile<32>(w.sG, 0, gh, g, t);
       store_tile<32>(w.sG2, 0, gu, g, t);
+    }
+    if (SPLIT) {
+      float *gdst = a.split_gh + (((int64_t)DEC * a.n_tiles + w.gtile) * 5 + i) * 1024;
+      store_tile<32>(gdst, 0, gh, g, t);
+      // relu mask of block i as one word per POINT (bit n = unit n): quad OR of the lane-layout bits
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pw = 0;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int e = 2 * (j & 1) + c2;
+            pw |= ((mk >> (((j >> 1) * 4 + nt) * 4 + e)) & 1u) << (8 * nt + 2 * t + c2);
+          }
+        pw |= __shfl_xor_sync(0xffffffffu, pw, 1);
+        pw |= __shfl_xor_sync(0xffffffffu, pw, 2);
+        if (t == j) a.split_mw[(((int64_t)DEC * a.n_tiles + w.gtile) * 5 + i) * 32 + g + 8 * j] = pw;
+      }
     }
     if (i == 3) { ENS_FOR_TILE(m, nt, e) gu3[m][nt][e] = gu[m][nt][e]; }
     gemm_hidden(gc, gh, L + PB::in_WcT(), g, t);                          // g_c += g_h Wc[:, :32]
@@ -474,6 +496,33 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
           }
         }
       }
+      if (SPLIT) {
+        // dB[r][32jc + col] = sum_pt p[pt][r] g_q[pt][col]: per-lane partial over its four rows, butterfly over the
+        // eight row groups, RED from the four lanes of row group 0
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int col = 32 * jc + 8 * nt + 2 * t + c2;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float q = acc[j >> 1][nt][2 * (j & 1) + c2];
+              s0 = fmaf(rx[j], q, s0); s1 = fmaf(ry[j], q, s1); s2 = fmaf(rz[j], q, s2);
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (g == 0 && col < EMB) {
+              atomicAdd(gdec + GO::off_B() + col, s0);
+              atomicAdd(gdec + GO::off_B() + EMB + col, s1);
+              atomicAdd(gdec + GO::off_B() + 2 * EMB + col, s2);
+            }
+          }
+      }
       if (WG) {
         store_tile<32>(w.sX, 0, ev, g, t);
         store_tile<RS>(w.crow, 0, acc, g, t);                              // g_q chunk (feature columns 0..31 are dead)
@@ -553,10 +602,10 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG, bool RECOMP>
-__global__ void __launch_bounds__(BwdCfg<STAGE, WG, RECOMP>::NT, BwdCfg<STAGE, WG, RECOMP>::MIN_CTAS)
+template <int STAGE, bool WG, bool RECOMP, bool SPLIT>
+__global__ void __launch_bounds__(BwdCfg<STAGE, WG, RECOMP, SPLIT>::NT, BwdCfg<STAGE, WG, RECOMP, SPLIT>::MIN_CTAS)
 render_bwd_mma_kernel(BwdArgs a) {
-  using CFG = BwdCfg<STAGE, WG, RECOMP>;
+  using CFG = BwdCfg<STAGE, WG, RECOMP, SPLIT>;
   constexpr int NT = CFG::NT;
   constexpr int RS = CFG::RS;
   extern __shared__ __align__(16) float smem[];
@@ -660,14 +709,19 @@ render_bwd_mma_kernel(BwdArgs a) {
   w.hs = (WG && RECOMP) ? a.hscratch + ((size_t)blockIdx.x * CFG::NW + w.warp) * 4096 : nullptr;
   w.gtile = (int64_t)blockIdx.x * CFG::NW + w.warp;
   if (WG) *reinterpret_cast<float4 *>(sP + threadIdx.x * 4) = make_float4(p32[0], p32[1], p32[2], 0.f);
+  if (SPLIT) {   // the points of this warp's tile, for the weight-gradient kernel (p.float() and normalised coordinates)
+    float4 *dst = reinterpret_cast<float4 *>(a.split_pts + (w.gtile * 32 + w.lane) * 8);
+    dst[0] = make_float4(p32[0], p32[1], p32[2], valid ? 1.f : 0.f);
+    dst[1] = make_float4(pn[0], pn[1], pn[2], 0.f);
+  }
 
   const float go1[1] = {g_occ};
-  decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+  decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
   if (STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR)
-    decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+    decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
   if (STAGE == ENS_STAGE_COLOR) {
     const float go4[4] = {g_rgb[0], g_rgb[1], g_rgb[2], 0.f};            // output 3 is overwritten (decoder.py:341)
-    decoder_bwd_mma<STAGE, WG, RECOMP, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
+    decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
   }
 
   // ---- points -> rays: g_o = sum_s g_p, g_d = sum_s z_s g_p ----
@@ -692,19 +746,251 @@ render_bwd_mma_kernel(BwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// weight-gradient kernel of the split mapping backward
+// ---------------------------------------------------------------------------------------------
+// grid (ctas, 3 decoders); a CTA of 8 warps walks its share of the 32-point tiles of ONE decoder and keeps the whole
+// decoder gradient in registers: the 30 (fine: 40) output strips of 16 x 32 -- dW_1..4, dWc_0..4, dW_0 and the
+// embedding half of dW_3 in three 32-column chunks each -- are dealt round-robin to the warps, each strip four
+// accumulator fragments.  Per tile: cp.async stages the five g_h tiles (from the data-gradient kernel), the
+// activation tiles h_0..h_3 (from the forward), the mask words and the points; the Fourier features are recomputed
+// (12 sines per thread) and the grid features re-gathered into shared tiles; then every warp runs its strips as
+// 3xTF32 m16n8k8 GEMMs over the 32 points (g_u = g_h masked on the fly by the per-point words).  RED.ADD once at the end.
+struct WgradArgs {
+  DevScene sc;
+  const float *gh;        // [3][stride][5][1024]
+  const uint32_t *mw;     // [3][stride][5][32]
+  const float *pts;       // [stride][32][8]
+  const float *save_h;    // [3][stride][5][1024]   (forward-saved)
+  int64_t n_tiles;        // tiles the data-gradient kernel wrote (its grid x 6 warps)
+  int64_t stride;         // tiles per decoder in gh / mw / save_h (the forward's tile count)
+  float *gdec[4];
+};
+
+template <int LDB, bool MASKED>
+__device__ __forceinline__ void wgrad_strip(float (&d)[4][4], float (&bsum)[2], const float *__restrict__ A,
+                                            const uint32_t *__restrict__ mwords, int m, const float *__restrict__ B,
+                                            int bcol0, int g, int t) {
+  const int sw = t << 3;
+  const int n0 = 16 * m + g, n1 = n0 + 8;
+  const int ac0 = n0 ^ sw, ac1 = n1 ^ sw;
+#pragma unroll
+  for (int pt0 = 0; pt0 < 32; pt0 += 8) {
+    const float *ar0 = A + (pt0 + t) * 32, *ar1 = ar0 + 4 * 32;
+    float a0 = ar0[ac0], a1 = ar0[ac1], a2 = ar1[ac0], a3 = ar1[ac1];
+    if (MASKED) {
+      const uint32_t w0 = mwords[pt0 + t], w1 = mwords[pt0 + t + 4];
+      a0 = ((w0 >> n0) & 1u) ? a0 : 0.f; a1 = ((w0 >> n1) & 1u) ? a1 : 0.f;
+      a2 = ((w1 >> n0) & 1u) ? a2 : 0.f; a3 = ((w1 >> n1) & 1u) ? a3 : 0.f;
+    }
+    bsum[0] += a0 + a2;
+    bsum[1] += a1 + a3;
+    uint32_t ah[4], al[4];
+    split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+    split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+    const float *br0 = B + (pt0 + t) * LDB, *br1 = br0 + 4 * LDB;
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int bc = (bcol0 + 8 * nt + g) ^ sw;
+      split_tf32(br0[bc], bh[nt][0], bl[nt][0]);
+      split_tf32(br1[bc], bh[nt][1], bl[nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(d[nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(d[nt], ah, bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(d[nt], ah, bh[nt][0], bh[nt][1]);
+  }
+}
+
+// trilinear features of FOUR points by one warp (8 lanes per point, 4 channels per lane), written to rows
+// 4*grp .. 4*grp+3 of a swizzled [32][RS] tile at columns c0..c0+31.  Same corner / fma order as gather_warp.
+template <int RS>
+__device__ __forceinline__ void gather_four(const float *__restrict__ grid, const int dims[3], const float *__restrict__ sPT,
+                                            int grp, float *__restrict__ crow, int c0, int lane) {
+  const int cq = lane & 7, pt = 4 * grp + (lane >> 3);
+  const float pn[3] = {sPT[pt * 8 + 4], sPT[pt * 8 + 5], sPT[pt * 8 + 6]};
+  const Vox v = make_vox(pn, dims);
+  const int X = dims[2], Y = dims[1], Z = dims[0];
+  const bool okx = v.x0 + 1 < X, oky = v.y0 + 1 < Y, okz = v.z0 + 1 < Z;
+  const float fx1 = okx ? v.fx : 0.f, fy1 = oky ? v.fy : 0.f, fz1 = okz ? v.fz : 0.f;
+  const int ox = okx ? C : 0, oy = oky ? X * C : 0, oz = okz ? X * Y * C : 0;
+  const float *p = grid + ((v.z0 * Y + v.y0) * X + v.x0) * C + 4 * cq;
+  float4 a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    a[c] = __ldg(reinterpret_cast<const float4 *>(p + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0)));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float w = __fmul_rn(__fmul_rn((c & 1) ? fx1 : v.gx, (c & 2) ? fy1 : v.gy), (c & 4) ? fz1 : v.gz);
+    r.x = fmaf(a[c].x, w, r.x); r.y = fmaf(a[c].y, w, r.y); r.z = fmaf(a[c].z, w, r.z); r.w = fmaf(a[c].w, w, r.w);
+  }
+  *reinterpret_cast<float4 *>(crow + pt * RS + ((c0 + 4 * cq) ^ ((pt & 3) << 3))) = r;
+}
+
+constexpr int WG_STAGE_FLOATS = 5 * 1024 + 4 * 1024 + 160 + 256;          // one staged tile: g_h, h_0..3, mask words, points
+
+template <int LEVEL, int CD, int NO>
+__device__ __forceinline__ void wgrad_decoder(const WgradArgs &a, float *__restrict__ smem) {
+  using GO = MlpGrad<CD, NO>;
+  constexpr int DEC = (LEVEL == ENS_LEVEL_MIDDLE) ? 0 : (LEVEL == ENS_LEVEL_FINE ? 1 : 2);
+  constexpr int NSTRIPS = 8 + 10 * (CD / 32) + 12;          // dW_1..4 | dWc (per 32 feature columns) | dW_0, dW_3e chunks
+  constexpr int PER_WARP = (NSTRIPS + 7) / 8;
+  float *sE = smem + 2 * WG_STAGE_FLOATS;          // [3][1024]   sin(p.B), 32-column chunks
+  float *sC = sE + 3 * 1024;                       // [32][CD]    features (swizzled rows)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const float *Bm = a.sc.w[LEVEL] + off_v2b<CD>() + MlpPackV2B::off_B();      // Fourier matrix [3][96]
+  float *gdec = a.gdec[LEVEL];
+
+  float acc[PER_WARP][4][4];
+  float bsum[PER_WARP][2];
+#pragma unroll
+  for (int q = 0; q < PER_WARP; ++q) {
+    bsum[q][0] = bsum[q][1] = 0.f;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[q][x][y] = 0.f;
+  }
+
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per, t1 = (t0 + per < a.n_tiles) ? t0 + per : a.n_tiles;
+
+  auto prefetch = [&](int64_t T, int buf) {        // cp.async the operands of tile T into stage buffer buf
+    float *st = smem + buf * WG_STAGE_FLOATS;
+    const float *gsrc = a.gh + ((int64_t)DEC * a.stride + T) * 5120;
+    const float *hsrc = a.save_h + ((int64_t)DEC * a.stride + T) * 5120;
+    const uint32_t s_gh = (uint32_t)__cvta_generic_to_shared(st), s_h = s_gh + 5 * 4096;
+    for (int i = tid; i < 1280; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_gh + i * 16), "l"(gsrc + i * 4) : "memory");
+    for (int i = tid; i < 1024; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_h + i * 16), "l"(hsrc + i * 4) : "memory");
+    if (tid < 40) {
+      const uint32_t *msrc = a.mw + ((int64_t)DEC * a.stride + T) * 160;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_h + 4 * 4096 + tid * 16), "l"(msrc + tid * 4) : "memory");
+    } else if (tid < 104) {
+      const float *psrc = a.pts + T * 256;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_h + 4 * 4096 + 640 + (tid - 40) * 16), "l"(psrc + (tid - 40) * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (t0 < t1) prefetch(t0, 0);
+  int buf = 0;
+  for (int64_t T = t0; T < t1; ++T, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                    // tile T staged; every warp is done with tile T-1 (stage buffer buf^1, sE, sC)
+    if (T + 1 < t1) prefetch(T + 1, buf ^ 1);                  // in flight during this tile's compute
+    const float *sGH = smem + buf * WG_STAGE_FLOATS;
+    const float *sH = sGH + 5 * 1024;
+    const uint32_t *sMW = reinterpret_cast<const uint32_t *>(sH + 4 * 1024);
+    const float *sPT = reinterpret_cast<const float *>(sMW + 160);
+    // ---- recompute the B operands that are cheap to recompute: Fourier features and grid features ----
+    {
+      const int pt = tid >> 3, c0 = (tid & 7) * 12;                 // 12 of the 96 columns of one point
+      const float px = sPT[pt * 8 + 0], py = sPT[pt * 8 + 1], pz = sPT[pt * 8 + 2];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int col = c0 + k;
+        const float q = fmaf(pz, __ldg(Bm + 2 * EMBP + col), fmaf(py, __ldg(Bm + EMBP + col), px * __ldg(Bm + col)));
+        sE[(col >> 5) * 1024 + pt * 32 + ((col & 31) ^ ((pt & 3) << 3))] = fast_sin(q);
+      }
+      gather_four<CD>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], sPT, warp, sC, 0, lane);     // warp w: points 4w..4w+3
+      if (CD == 64)                                                                   // fine decoder: [fine | middle]
+        gather_four<CD>(a.sc.grid[ENS_LEVEL_MIDDLE], a.sc.dims[ENS_LEVEL_MIDDLE], sPT, warp, sC, 32, lane);
+    }
+    __syncthreads();
+    // ---- the strips of this warp ----
+#pragma unroll
+    for (int q = 0; q < PER_WARP; ++q) {
+      const int id = warp + 8 * q;
+      if (id >= NSTRIPS) break;
+      const int m = id & 1;
+      if (id < 8) {                                   // dW_i, i = 1..4:  g_u_i^T h_{i-1}
+        const int i = 1 + (id >> 1);
+        wgrad_strip<32, true>(acc[q], bsum[q], sGH + i * 1024, sMW + i * 32, m, sH + (i - 1) * 1024, 0, g, t);
+      } else if (id < 8 + 10 * (CD / 32)) {           // dWc_i, i = 0..4, 32 feature columns per strip pair:  g_h_i^T c
+        const int r = id - 8, i = (r >> 1) % 5, half = r / 10;
+        wgrad_strip<CD, false>(acc[q], bsum[q], sGH + i * 1024, nullptr, m, sC, 32 * half, g, t);
+      } else {                                        // dW_0 / dW_3 (embedding half), chunk jc:  g_u^T e
+        const int r = id - (8 + 10 * (CD / 32)), which = r / 6, jc = (r % 6) >> 1;
+        const int i = which ? 3 : 0;
+        wgrad_strip<32, true>(acc[q], bsum[q], sGH + i * 1024, sMW + i * 32, m, sE + jc * 1024, 0, g, t);
+      }
+    }
+  }
+  // ---- emit ----
+#pragma unroll
+  for (int q = 0; q < PER_WARP; ++q) {
+    const int id = warp + 8 * q;
+    if (id >= NSTRIPS) break;
+    const int m = id & 1;
+    if (id < 8) {
+      const int i = 1 + (id >> 1), K = (i == 3) ? 125 : 32;
+      float *out = gdec + grad_off_W<CD, NO>(i);
+      emit_strip<4>(out, K, (i == 3) ? EMB : 0, 32, m, acc[q], g, t);
+      emit_bias(out + 32 * K, m, bsum[q], g, t);
+    } else if (id < 8 + 10 * (CD / 32)) {
+      const int r = id - 8, i = (r >> 1) % 5, half = r / 10;
+      float *out = gdec + GO::off_Wc(0) + i * (32 * CD + 32);
+      emit_strip<4>(out, CD, 32 * half, 32, m, acc[q], g, t);
+      if (half == 0) emit_bias(out + 32 * CD, m, bsum[q], g, t);
+    } else {
+      const int r = id - (8 + 10 * (CD / 32)), which = r / 6, jc = (r % 6) >> 1;
+      if (which == 0) {
+        float *out = gdec + GO::off_W(0);
+        emit_strip<4>(out, EMB, 32 * jc, EMB - 32 * jc, m, acc[q], g, t);
+        if (jc == 0) emit_bias(out + 32 * EMB, m, bsum[q], g, t);
+      } else {
+        emit_strip<4>(gdec + GO::off_W(3), 125, 32 * jc, EMB - 32 * jc, m, acc[q], g, t);
+      }
+    }
+  }
+}
+
+constexpr int WGRAD_SMEM_FLOATS = 2 * WG_STAGE_FLOATS + 3 * 1024 + 32 * 64;
+
+template <int STAGE>
+__global__ void __launch_bounds__(256, 2) wgrad_split_kernel(WgradArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  if (blockIdx.y == 0) wgrad_decoder<ENS_LEVEL_MIDDLE, 32, 1>(a, smem);
+  else if (blockIdx.y == 1) { if (STAGE >= ENS_STAGE_FINE) wgrad_decoder<ENS_LEVEL_FINE, 64, 1>(a, smem); }
+  else { if (STAGE == ENS_STAGE_COLOR) wgrad_decoder<ENS_LEVEL_COLOR, 32, 4>(a, smem); }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-template <int STAGE, bool WG, bool RECOMP>
+template <int STAGE, bool WG, bool RECOMP, bool SPLIT>
 static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
-  using CFG = BwdCfg<STAGE, WG, RECOMP>;
+  using CFG = BwdCfg<STAGE, WG, RECOMP, SPLIT>;
   a.ra.rpc = CFG::NT / a.ra.S;
   const size_t smem = CFG::smem_bytes();
-  if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG, RECOMP, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ENS_ECUDA;
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
-  render_bwd_mma_kernel<STAGE, WG, RECOMP><<<g, CFG::NT, smem, s>>>(a);
+  render_bwd_mma_kernel<STAGE, WG, RECOMP, SPLIT><<<g, CFG::NT, smem, s>>>(a);
   ENS_CHECK_CUDA();
   return ENS_OK;
+}
+
+static bool use_split_backward() {
+  const char *v = std::getenv("ENS_BWD_SPLIT");
+  return !(v && v[0] == '0');
+}
+
+// layout of the split scratch inside the caller's workspace; every per-decoder array uses the FORWARD's tile count as
+// its stride (the data-gradient kernel indexes the forward-saved buffers and the scratch with the same a.n_tiles)
+static void split_layout(int64_t n_rays, int S, int64_t *stride, int64_t *off_mw, int64_t *off_pts, int64_t *total) {
+  const int rpc_f = NT_MMA / S;
+  const int64_t nt = ((n_rays + rpc_f - 1) / rpc_f) * (NT_MMA / 32);
+  const int64_t gh = 3 * nt * 5120 * 4, mw = 3 * nt * 160 * 4, pts = nt * 256 * 4;
+  if (stride) *stride = nt;
+  if (off_mw) *off_mw = gh;
+  if (off_pts) *off_pts = gh + mw;
+  if (total) *total = gh + mw + pts;
 }
 
 template <int STAGE>
@@ -712,11 +998,37 @@ static int launch_bwd_mma_any(BwdArgs &a, bool wg, cudaStream_t s) {
   // the saved-forward fast path needs the masks, the activation tiles when decoder gradients are wanted, and a
   // samples-per-ray count that tiles the 192-thread CTAs (so forward and backward agree on the 32-point tiles)
   const bool saved = a.save_masks != nullptr && (192 % a.ra.S) == 0 && (!wg || a.save_h != nullptr);
-  if (saved) return wg ? launch_bwd_mma<STAGE, true, false>(a, s) : launch_bwd_mma<STAGE, false, false>(a, s);
-  return wg ? launch_bwd_mma<STAGE, true, true>(a, s) : launch_bwd_mma<STAGE, false, true>(a, s);
+  if (!saved) return wg ? launch_bwd_mma<STAGE, true, true, false>(a, s) : launch_bwd_mma<STAGE, false, true, false>(a, s);
+  if (!wg) return launch_bwd_mma<STAGE, false, false, false>(a, s);
+  if (!use_split_backward() || a.hscratch == nullptr) return launch_bwd_mma<STAGE, true, false, false>(a, s);
+  // split mapping backward: data gradients at two CTAs per SM, then the weight-gradient GEMMs
+  int64_t stride, off_mw, off_pts;
+  split_layout(a.ra.R, a.ra.S, &stride, &off_mw, &off_pts, nullptr);
+  if (stride != a.n_tiles) return ENS_ESHAPE;            // must be the forward's tile count
+  char *base = reinterpret_cast<char *>(a.hscratch);
+  a.split_gh = reinterpret_cast<float *>(base);
+  a.split_mw = reinterpret_cast<uint32_t *>(base + off_mw);
+  a.split_pts = reinterpret_cast<float *>(base + off_pts);
+  const int rpc_b = 192 / a.ra.S;
+  const int64_t tiles = ((a.ra.R + rpc_b - 1) / rpc_b) * 6;   // what the data-gradient grid covers (<= stride)
+  WgradArgs wa;
+  wa.sc = a.sc; wa.gh = a.split_gh; wa.mw = a.split_mw; wa.pts = a.split_pts; wa.save_h = a.save_h;
+  wa.n_tiles = tiles; wa.stride = stride;
+  for (int l = 0; l < 4; ++l) wa.gdec[l] = a.gdec[l];
+  int rc = launch_bwd_mma<STAGE, false, false, true>(a, s);
+  if (rc != ENS_OK) return rc;
+  const size_t smem = (size_t)WGRAD_SMEM_FLOATS * 4;
+  if (cudaFuncSetAttribute(wgrad_split_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  const int ndec = (STAGE == ENS_STAGE_MIDDLE) ? 1 : (STAGE == ENS_STAGE_FINE ? 2 : 3);
+  int64_t ctas = 296 / ndec;
+  if (ctas > tiles) ctas = tiles;
+  wgrad_split_kernel<STAGE><<<dim3((unsigned)ctas, ndec), 256, smem, s>>>(wa);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
 }
 
 int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s) {
+  a.split_gh = nullptr; a.split_mw = nullptr; a.split_pts = nullptr;
   switch (stage) {
     case ENS_STAGE_MIDDLE: return launch_bwd_mma_any<ENS_STAGE_MIDDLE>(a, wg, s);
     case ENS_STAGE_FINE: return launch_bwd_mma_any<ENS_STAGE_FINE>(a, wg, s);
@@ -725,12 +1037,16 @@ int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s) {
   }
 }
 
-// scratch of the WG instantiation: 4 tiles of 4 KB per warp, 6 warps per CTA of 192 / S rays
+// scratch: the recompute variant needs 4 tiles of 4 KB per warp (6 warps per CTA of 192 / S rays); the split variant
+// the g_h tiles, mask words and points of every tile
 int64_t mma_bwd_workspace_bytes(int64_t n_rays, int S) {
   const int rpc = 192 / S;
   if (rpc < 1) return 0;
   const int64_t ctas = (n_rays + rpc - 1) / rpc;
-  return ctas * 6 * 4096 * (int64_t)sizeof(float);
+  const int64_t recompute = ctas * 6 * 4096 * (int64_t)sizeof(float);
+  int64_t split = 0;
+  if ((192 % S) == 0) split_layout(n_rays, S, nullptr, nullptr, nullptr, &split);
+  return recompute > split ? recompute : split;
 }
 
 }  // namespace ens

@@ -221,7 +221,9 @@ class _RenderBatchRay(torch.autograd.Function):
         saved = ctx.saved_fwd
         if saved is not None and any_param and not ctx.saved_has_h:
             saved = None                      # activations were not kept: let the kernel recompute
-        ws_bytes = 0 if saved is not None else int(L.ens_bwd_workspace_bytes(R, S, 1 if any_param else 0))
+        # scratch: the recompute variant spills activations there; with a saved forward it carries the g_h tiles from
+        # the data-gradient kernel to the weight-gradient kernel (split mapping backward)
+        ws_bytes = int(L.ens_bwd_workspace_bytes(R, S, 1 if any_param else 0))
         ws = torch.empty(max(ws_bytes, 4) // 4, dtype=torch.float32, device=dev) if ws_bytes else None
         sc = build_scene_struct(setup.bound, setup.coarse_bound, ctx.native, ctx.packed)
         cfg = setup.cfg_struct()
