@@ -362,7 +362,7 @@ def run_gpu_arm(args):
         n_b, t_b = ksum.get("render_bwd", (0, float("nan")))
         n_f, t_f = ksum.get("render_fwd", (0, float("nan")))
         achieved = BYTES_PER_POINT_BWD * N_RAYS * S_TOTAL / (t_b * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "render_bwd_mma_kernel<color, wgrad>", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "ens_render_bwd: render_bwd_mma_kernel<color, split> + wgrad_split_kernel<color>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "peak_source": peak_src, "kernel_ms": t_b, "kernel_share_of_step": t_b / ms_per_step,
                 "fwd_kernel_ms": t_f, "fwd_achieved_gbs": BYTES_PER_POINT_FWD * N_RAYS * S_TOTAL / (t_f * 1e-3) / 1e9,

@@ -371,14 +371,22 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   if (WG) cp_async_tile(w.sX, hsrc + 3 * 1024, lane);                     // x_4 = h_3
 
   // ---- 4. blocks 4..0 ----
+  // PARK_GC: in the two-CTA/SM variants (168 registers) the running feature gradient g_c lives in the warp's -- then
+  // idle -- feature tile between blocks instead of in 32 registers; after block 0 the tile is what step 5 wants anyway.
+  constexpr bool PARK_GC = !WG && !RECOMP;
   float gc[2][4][4], gu[2][4][4], gu3[2][4][4];
-  zero_tile(gc);
+  if (!PARK_GC) zero_tile(gc);
 #pragma unroll 1
   for (int i = 4; i >= 0; --i) {
     const float *L = sw + PB::off_L(0) + i * 2048;
     uint32_t mk = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) if (k == i) mk = mask[k];
+    if (PARK_GC) {
+      if (i == 4) zero_tile(gc); else load_tile<RS>(w.crow, 0, gc, g, t);
+      gemm_hidden(gc, gh, L + PB::in_WcT(), g, t);                        // g_c += g_h Wc[:, :32]
+      store_tile<RS>(w.crow, 0, gc, g, t);
+    }
     ENS_FOR_TILE(m, nt, e) gu[m][nt][e] = ((mk >> ((m * 4 + nt) * 4 + e)) & 1u) ? gh[m][nt][e] : 0.f;
     if (WG) {
       store_tile<32>(w.sG, 0, gh, g, t);
@@ -404,7 +412,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
       }
     }
     if (i == 3) { ENS_FOR_TILE(m, nt, e) gu3[m][nt][e] = gu[m][nt][e]; }
-    gemm_hidden(gc, gh, L + PB::in_WcT(), g, t);                          // g_c += g_h Wc[:, :32]
+    if (!PARK_GC) gemm_hidden(gc, gh, L + PB::in_WcT(), g, t);            // g_c += g_h Wc[:, :32]
     if (i > 0) {
       zero_tile(gh);
       gemm_hidden(gh, gu, L + PB::in_WhT(), g, t);                        // g_h_{i-1} = g_u W_i (hidden part)
@@ -447,7 +455,7 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
   // ---- 5. trilinear backward ----
   if (ggrid != nullptr || want_rays) {
     __syncwarp();
-    store_tile<RS>(w.crow, 0, gc, g, t);
+    if (!PARK_GC) store_tile<RS>(w.crow, 0, gc, g, t);
     __syncwarp();
     float gpn[3];
     gather_bwd_warp<RS>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], v, valid, w.crow, want_rays, gpn);
