@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import LEVELS, STAGES, STAGE_LEVELS, EnsGrads, EnsRenderCfg
-from .scene import SceneCache, build_scene_struct, decoder_grad_views
+from .scene import SceneCache, build_scene_struct, decoder_grad_views, is_native_strided
 
 
 SAVE_FORWARD = True    # keep relu masks / activations from the forward kernel for the backward (False: it recomputes)
@@ -154,6 +154,7 @@ class _RenderBatchRay(torch.autograd.Function):
             int(want_dec), stream)), "ens_render_fwd")
         ctx.saved_fwd = saved
         ctx.saved_has_h = bool(want_dec)
+        ctx.grid_native_strided = [is_native_strided(g) for g in grids]
         ctx.setup = setup
         ctx.levels = levels
         ctx.n_grids = n_grids
@@ -243,7 +244,10 @@ class _RenderBatchRay(torch.autograd.Function):
         out.append(g_ro if need_ro else None)
         out.append(g_rd if need_rd else None)
         for gi, lv in enumerate(levels):
-            if need_grid[gi]:
+            if need_grid[gi] and ctx.grid_native_strided[gi]:
+                # the grid lives in the kernels' layout: hand autograd a [1,32,Z,Y,X] view of the native gradient
+                out.append(g_native[lv].permute(3, 0, 1, 2).unsqueeze(0))
+            elif need_grid[gi]:
                 nat = g_native[lv]
                 Z, Y, X = nat.shape[:3]
                 g_ref = torch.empty((1, 32, Z, Y, X), dtype=torch.float32, device=dev)

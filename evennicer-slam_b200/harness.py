@@ -25,7 +25,7 @@ def default_cfg() -> dict:
     }
 
 
-def build(scene: syn.Scene, device="cuda:0", cfg=None, requires_grad: bool = True):
+def build(scene: syn.Scene, device="cuda:0", cfg=None, requires_grad: bool = True, native_layout: bool = False):
     """(decoders: NICE, c: dict of grids, renderer: Renderer, cfg)."""
     from .decoder import NICE
     from .renderer import Renderer
@@ -47,6 +47,9 @@ def build(scene: syn.Scene, device="cuda:0", cfg=None, requires_grad: bool = Tru
     for p in decoders.parameters():
         p.requires_grad_(requires_grad)
     c = {k: torch.from_numpy(v.copy()).to(device) for k, v in scene.grids.items()}
+    if native_layout:       # grids allocated in the kernels' layout, exposed as [1,32,Z,Y,X] views (scene.as_native_layout)
+        from .scene import as_native_layout
+        c = {k: as_native_layout(v) for k, v in c.items()}
     cam = scene.cam
     slam = types.SimpleNamespace(nice=True, bound=bound, H=cam.H, W=cam.W, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy)
     renderer = Renderer(cfg, None, slam)

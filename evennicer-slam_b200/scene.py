@@ -42,6 +42,30 @@ def decoder_grad_views(flat: torch.Tensor, params: Sequence[torch.Tensor]):
     return out
 
 
+def is_native_strided(grid: torch.Tensor) -> bool:
+    """True if ``grid`` ([1,32,Z,Y,X]) is a view of a contiguous [Z,Y,X,32] buffer -- the layout the kernels read."""
+    if grid.dim() != 5 or grid.shape[0] != 1:
+        return False
+    _, Cc, Z, Y, X = grid.shape
+    return tuple(grid.stride()[1:]) == (1, Y * X * Cc, X * Cc, Cc)
+
+
+def as_native_layout(grid: torch.Tensor) -> torch.Tensor:
+    """Re-allocate a feature grid in the kernels' layout and return it as a [1,32,Z,Y,X] VIEW.
+
+    Logically identical to the input (same shape, values, dtype): every caller of the reference keeps working
+    (boolean-mask indexing, in-place index_put, clone, share_memory_, torch.save), but the renderer then reads the
+    storage directly and returns gradients as views of its native gradient buffer -- no layout conversion per
+    iteration.  One line after ``grid_init`` (EvenNICER_SLAM.py:217-275); see INTEGRATION.md.
+    """
+    if is_native_strided(grid):
+        return grid
+    g = grid.detach()
+    native = g[0].permute(1, 2, 3, 0).contiguous()            # [Z,Y,X,32]
+    out = native.permute(3, 0, 1, 2).unsqueeze(0)             # [1,32,Z,Y,X] view
+    return out.requires_grad_(grid.requires_grad)
+
+
 class _GridEntry:
     __slots__ = ("ref", "version", "native")
 
@@ -71,6 +95,9 @@ class SceneCache:
             raise ValueError(f"grid_{level} must be [1,32,Z,Y,X], got {tuple(grid.shape)}")
         if grid.dtype != torch.float32 or not grid.is_cuda:
             raise ValueError(f"grid_{level} must be a float32 CUDA tensor")
+        if is_native_strided(grid):                 # already in the kernels' layout: no copy, nothing to cache
+            self.stats["grid_hit"] += 1
+            return grid.detach()[0].permute(1, 2, 3, 0)
         key = (level, grid.device.index)
         e = self._grids.get(key)
         if e is not None and e.ref() is grid and e.version == grid._version:

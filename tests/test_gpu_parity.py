@@ -431,6 +431,49 @@ def test_room0_mapping_batch_vs_golden_and_oracle():
         assert int((flat != 0).sum()) == int(g[f"ggrid.{gk}.nnz"])
 
 
+def test_native_layout_grids_are_equivalent(tiny):
+    """Grids re-allocated with scene.as_native_layout (a [1,32,Z,Y,X] VIEW of the kernels' [Z,Y,X,32] storage) give
+    bit-identical outputs, the same gradients, need no layout conversion, and keep working with the callers' idioms
+    (boolean-mask indexing and in-place masked writes, Mapper.py:343-361, 451-458)."""
+    from evennicer_slam_b200.scene import as_native_layout, is_native_strided
+    renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
+    tag = "color.d"
+    for p in decoders.parameters():
+        p.requires_grad_(True)
+    outs = []
+    for native in (False, True):
+        for p in decoders.parameters():
+            p.grad = None
+        cg = {k: (as_native_layout(v.clone()) if native else v.clone()).requires_grad_(True) for k, v in c.items()}
+        if native:
+            assert all(is_native_strided(v) and v.shape == c[k].shape and torch.equal(v, c[k]) for k, v in cg.items())
+        ro = torch.from_numpy(g[f"{tag}.rays_o"]).to(DEV).requires_grad_(True)
+        rd = torch.from_numpy(g[f"{tag}.rays_d"]).to(DEV).requires_grad_(True)
+        sd = torch.from_numpy(g[f"{tag}.sample_depth"]).to(DEV)
+        before = dict(renderer._cache.stats)
+        depth, var, color = renderer.render_batch_ray(cg, decoders, rd, ro, DEV, "color", gt_depth=sd)
+        if native:
+            assert renderer._cache.stats["grid_convert"] == before["grid_convert"]      # nothing was re-laid-out
+        g_d, g_v, g_c = cases.upstream_grads(ro.shape[0])
+        ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+         + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+        outs.append((depth.detach(), color.detach(), {k: v.grad for k, v in cg.items()}, rd.grad))
+    (d0, c0, gg0, r0), (d1, c1, gg1, r1) = outs
+    assert torch.equal(d0, d1) and torch.equal(c0, c1)
+    for k in ("grid_middle", "grid_fine", "grid_color"):
+        assert gg1[k].shape == gg0[k].shape
+        assert rel_err(gg1[k].cpu().numpy(), gg0[k].cpu().numpy()) < 1e-5
+        assert rel_err(gg1[k].cpu().numpy(), g[f"{tag}.ggrid.{k}"]) < TOL_GRAD
+    assert rel_err(r1.cpu().numpy(), r0.cpu().numpy()) < 1e-5
+    # the Mapper's masked read / write idiom on a native-layout grid
+    val = as_native_layout(c["grid_fine"].clone())
+    mask = torch.rand(val.shape, device=DEV) > 0.5
+    sel = val[mask].clone()
+    assert torch.equal(sel, c["grid_fine"][mask])
+    val[mask] = sel * 2
+    assert torch.equal(val[mask], c["grid_fine"][mask] * 2) and is_native_strided(val)
+
+
 def test_scene_cache_tracks_in_place_updates(tiny):
     """Mapper mutates grids in place every iteration (Mapper.py:451-458): results must follow."""
     renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
