@@ -474,6 +474,44 @@ def test_native_layout_grids_are_equivalent(tiny):
     assert torch.equal(val[mask], c["grid_fine"][mask] * 2) and is_native_strided(val)
 
 
+def test_rpg_sized_grids_larger_than_l2():
+    """RPG recording4 bounds with the 346 x 260 camera (configs/rpg/rpg.yaml:62-71): 197 MiB of grids, more than the
+    126 MB L2.  A 200-ray colour-stage batch forward + backward against the oracle (per-ray quantities robustly: the
+    case is not kink-screened), plus sanity on the dense grid gradient."""
+    import evennicer_slam_b200.synthetic as syn
+    from evennicer_slam_b200 import harness, common
+    scene = syn.make_scene(syn.RPG4_BOUND, syn.RPG_CAM, seed=cases.SEED, name="rpg4", grid_std={"fine": 0.01})
+    assert sum(v.nbytes for v in scene.grids.values()) > 190 << 20
+    decoders, c, renderer, cfg = harness.build(scene, DEV)
+    cam = scene.cam
+    cam_t = syn.default_pose(syn.RPG4_BOUND, jitter_seed=3)
+    depth, color, _ = syn.synthetic_frame(syn.RPG4_BOUND, cam, cam_t, seed=5, zero_frac=0.02)
+    torch.manual_seed(11)
+    c2w = common.get_camera_from_tensor(torch.from_numpy(cam_t.copy()).to(DEV))
+    ro, rd, sd, _ = common.get_samples(0, cam.H, 0, cam.W, 200, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w,
+                                       torch.from_numpy(depth).to(DEV), torch.from_numpy(color).to(DEV), DEV)
+    ro = ro.detach().requires_grad_(True); rd = rd.detach().requires_grad_(True)
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    d, u, col, raw, z, w = renderer.render_batch_ray_aux(cg, decoders, rd, ro, DEV, "color", gt_depth=sd)
+    g_d, g_v, g_c = cases.upstream_grads(200)
+    ((d * torch.from_numpy(g_d).to(DEV)).sum() + (u * torch.from_numpy(g_v).to(DEV)).sum()
+     + (col.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    sc = orc.OracleScene.from_synthetic(scene)
+    t32 = torch.linspace(0., 1., 32).numpy(); t64 = torch.linspace(0., 1., 16).double().numpy()
+    od, ov, oc, cache = orc.render_batch_ray(sc, ro.detach().cpu().numpy(), rd.detach().cpu().numpy(), "color",
+                                             sd.cpu().numpy(), t32, t64)
+    assert np.array_equal(z.cpu().numpy(), cache["z"])
+    assert rel_err(d.detach().cpu().numpy(), od) < TOL_OUT and rel_err(col.detach().cpu().numpy(), oc) < TOL_OUT
+    og = orc.render_batch_ray_backward(sc, cache, g_d, g_v, g_c)
+    for got, ref in ((ro.grad.cpu().numpy(), og["rays_o"]), (rd.grad.cpu().numpy(), og["rays_d"])):
+        per_ray = np.abs(got - ref).max(axis=1) / np.abs(ref).max()
+        assert (per_ray < TOL_GRAD).mean() >= 0.98 and per_ray.max() < 2e-2
+    for k in ("grid_middle", "grid_fine", "grid_color"):
+        gg = cg[k].grad.cpu().numpy()
+        assert rel_err(gg, og["grids"][k]) < TOL_GRAD_KINK, k
+        assert int((gg != 0).sum()) == int((og["grids"][k] != 0).sum()), k
+
+
 def test_scene_cache_tracks_in_place_updates(tiny):
     """Mapper mutates grids in place every iteration (Mapper.py:451-458): results must follow."""
     renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
