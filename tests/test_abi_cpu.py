@@ -35,7 +35,15 @@ def test_sizes_match_reference_parameter_counts(built):
     assert [L.ens_decoder_num_tensors(i) for i in range(4)] == [12, 23, 23, 23]
     assert L.ens_packed_decoder_floats(1) % 4 == 0 and L.ens_packed_decoder_floats(2) % 4 == 0
     assert L.ens_bwd_workspace_bytes(1000, 48, 0) == 0
-    assert L.ens_bwd_workspace_bytes(1000, 48, 1) == (48000 + 1) * 160 * 4
+    # 1000 rays x 48 samples = 1500 tiles of 32 points: split-backward scratch = g_h tiles (3 decoders x 5 x 4 KB per
+    # tile) + mask words (3 x 5 x 128 B) + points (1 KB); it exceeds the recompute / FFMA activation scratch
+    assert L.ens_bwd_workspace_bytes(1000, 48, 1) == 1500 * (3 * 5 * 4096 + 3 * 5 * 128 + 1024)
+    assert L.ens_bwd_workspace_bytes(1000, 48, 1) >= (48000 + 1) * 160 * 4
+    # saved-for-backward buffer of the forward: masks only / masks + five activation tiles per decoder
+    assert L.ens_fwd_saved_bytes(1000, 48, 3, 0) == 3 * 1500 * 5 * 128
+    assert L.ens_fwd_saved_bytes(1000, 48, 3, 1) == 3 * 1500 * 5 * 128 + 3 * 1500 * 5 * 4096
+    assert L.ens_fwd_saved_bytes(1000, 48, 0, 1) == 0            # coarse stage: FFMA kernels, nothing saved
+    assert L.ens_fwd_saved_bytes(1000, 40, 3, 1) == 0            # 40 samples per ray do not tile the CTAs
     import evennicer_slam_b200.synthetic as syn
     for li, lv in enumerate(syn.LEVELS):
         n = sum(int(np.prod(s)) for _, s in syn.decoder_param_shapes(lv))
