@@ -258,6 +258,9 @@ def run_gpu_arm(args):
     scene, frames = make_inputs()
     decoders, c, renderer, cfg = harness.build(scene, dev, native_layout=not args.reference_grid_layout)
     cam = scene.cam
+    # config 4 sharded over the ranks -- measured first, before any collective has been captured into a CUDA graph
+    # (eager NCCL calls issued after such a capture were seen to run several times slower)
+    sharded = measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world) if (world > 1 and not args.no_other_configs) else None
     depth_t = [torch.from_numpy(d).to(dev) for (_, d, _) in frames]
     color_t = [torch.from_numpy(col).to(dev) for (_, _, col) in frames]
     cams = [torch.from_numpy(ct.copy()).to(dev) for (ct, _, _) in frames]
@@ -271,15 +274,29 @@ def run_gpu_arm(args):
         for t in cam_params + list(grids.values()) + params:
             t.grad = None
 
+    # The per-keyframe chains (camera tensor -> c2w -> pixel draw -> rays, and their backward into the camera tensors)
+    # are independent of each other: each runs on its own stream, so the captured graph has five parallel branches
+    # instead of ~35 tiny kernels in a row (autograd replays every backward node on its forward stream).
+    side = [torch.cuda.Stream(dev) for _ in range(N_FRAMES)] if args.frame_streams else None
+
     def step():
         renderer._cache.invalidate()
-        ros, rds, sds, scs = [], [], [], []
+        ros, rds, sds, scs = [None] * N_FRAMES, [None] * N_FRAMES, [None] * N_FRAMES, [None] * N_FRAMES
+        cur = torch.cuda.current_stream(dev)
         for f in range(N_FRAMES):
-            ct = cams[0] if f == 0 else cam_params[f - 1]
-            c2w = common.get_camera_from_tensor(ct)
-            ro, rd, sd, sc_ = common.get_samples(0, cam.H, 0, cam.W, PIX_PER_FRAME, cam.H, cam.W, cam.fx, cam.fy,
-                                                 cam.cx, cam.cy, c2w, depth_t[f], color_t[f], dev)
-            ros.append(ro.float()); rds.append(rd.float()); sds.append(sd.float()); scs.append(sc_.float())
+            if side is not None:
+                side[f].wait_stream(cur)
+            with torch.cuda.stream(side[f] if side is not None else cur):
+                ct = cams[0] if f == 0 else cam_params[f - 1]
+                c2w = common.get_camera_from_tensor(ct)
+                ro, rd, sd, sc_ = common.get_samples(0, cam.H, 0, cam.W, PIX_PER_FRAME, cam.H, cam.W, cam.fx, cam.fy,
+                                                     cam.cx, cam.cy, c2w, depth_t[f], color_t[f], dev)
+                ros[f], rds[f], sds[f], scs[f] = ro.float(), rd.float(), sd.float(), sc_.float()
+        if side is not None:
+            for f in range(N_FRAMES):
+                cur.wait_stream(side[f])
+                for t in (ros[f], rds[f], sds[f], scs[f]):
+                    t.record_stream(cur)
         ro, rd, sd, sc_ = torch.cat(ros), torch.cat(rds), torch.cat(sds), torch.cat(scs)
         depth, unc, color = renderer.render_batch_ray(grids, decoders, rd, ro, dev, "color", gt_depth=sd)
         # Mapper.py:553-562: sum|gt-d|[gt>0] + 0.2*sum|gt_c-c| ; the mask is applied by where() instead of
@@ -358,6 +375,8 @@ def run_gpu_arm(args):
     # ---- tracking iteration (config C2), reported beside the headline ----
     track_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
     other = measure_other_configs(dev, renderer, decoders, c, frames, scene) if (rank == 0 and not args.no_other_configs) else None
+    if other is not None and sharded is not None:
+        other["full_frame_sharded"] = sharded
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -523,6 +542,50 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
     return tot / iters
 
 
+def measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world):
+    """Config 4 on N GPUs (all ranks call this): the 816 000-ray frame in the reference's 100 000-ray batches, every
+    batch split over the ranks (replicated scene, the two batch-global depth maxima MAX-reduced, outputs all-gathered,
+    sharding.render_rays_sharded).  Also checks, on real NCCL, that one sharded batch equals the unsharded render
+    bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from evennicer_slam_b200 import common, sharding
+    cam = scene.cam
+    cam_t, depth, color = frames[-1]
+    depth_t = torch.from_numpy(depth).to(dev).reshape(-1)
+    req = [p.requires_grad for p in decoders.parameters()]
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+    with torch.no_grad():
+        c2w = common.get_camera_from_tensor(torch.from_numpy(cam_t.copy()).to(dev))
+        ro, rd = common.get_rays(cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w, dev)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        B = renderer.ray_batch_size
+
+        def frame():
+            outs = []
+            for i in range(0, ro.shape[0], B):
+                outs.append(sharding.render_rays_sharded(renderer, c, decoders, rd[i:i + B], ro[i:i + B], dev, "color",
+                                                         gt_depth=depth_t[i:i + B]))
+            return outs
+        outs = frame()
+        ref = renderer.render_batch_ray(c, decoders, rd[:B], ro[:B], dev, "color", gt_depth=depth_t[:B])
+        same = all(bool(torch.equal(a, b)) for a, b in zip(outs[0], ref))
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            frame()
+        b.record(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / 2], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for p, r in zip(decoders.parameters(), req):
+        p.requires_grad_(r)
+    ms = float(t.item())
+    n = cam.H * cam.W
+    return {"rays": n, "n_gpus": world, "ms": ms, "rays_per_s": n / ms * 1e3, "equals_unsharded_bitwise": same}
+
+
 def measure_other_configs(dev, renderer, decoders, c, frames, scene):
     """Reported beside the headline (BASELINE.json configs 2, 4, 5): CUDA-event times, inputs resident.
 
@@ -600,6 +663,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the event-render / full-frame / mesh timings")
+    ap.add_argument("--no-frame-streams", dest="frame_streams", action="store_false",
+                    help="keep the five per-keyframe get_samples chains on one stream (default: five streams = parallel "
+                         "branches of the captured graph)")
     ap.add_argument("--reference-grid-layout", action="store_true",
                     help="keep the grids as contiguous [1,32,Z,Y,X] tensors (re-laid-out every step) instead of "
                          "[1,32,Z,Y,X] views of native [Z,Y,X,32] storage (scene.as_native_layout)")
