@@ -158,21 +158,25 @@ struct CoarseGrad {
 //     element (n, k) at  (n/8)*(K/4)*32 + (k/4)*32 + (n%8)*4 + (k%4)   floats      (SBO = (K/4)*128 B, LBO = 128 B)
 // twice: the value itself (the tensor core reads its top 19 bits = the TF32 "hi" part) and, TOT floats further,
 // the remainder  lo = w - tf32_trunc(w)  for the 3xTF32 passes.
-//   matrices, in order: W0 [32][96], W3e [32][96], Wh_1, Wh_2, Wh_3 (hidden part), Wh_4 [32][32], Wc_0..Wc_4 [32][CD]
-//   then: B [3][96], b_i [5][32], bc_i [5][32], Wo [4][32] (rows >= NO zero), bo [4]
+// The feature injection of block i is folded into block i+1 (h_i = relu(u_i) + Wc_i c + bc_i enters only through
+// W_{i+1} h_i), so no separate feature accumulator is needed in TMEM:
+//     u_{i+1} = W_{i+1} relu(u_i) + M_i c + b'_{i+1},   M_i = W_{i+1}[hidden] Wc_i,   b'_{i+1} = W_{i+1}[hidden] bc_i + b_{i+1}
+//     out     = Wo relu(u_4) + Mo c + bo',              Mo  = Wo Wc_4,                bo' = Wo bc_4 + bo
+//   matrices, in order: W0 [32][96], W3e [32][96], Wh_1, Wh_2, Wh_3 (hidden part), Wh_4 [32][32], M_0..M_3 [32][CD]
+//   then: B [3][96], b'_i [5][32], Wo [4][32] (rows >= NO zero), Mo [4][CD], bo' [4]
 // ---------------------------------------------------------------------------------------------
 template <int CD>
 struct MlpPackTC {
   __host__ __device__ static constexpr int off_W0() { return 0; }
   __host__ __device__ static constexpr int off_W3e() { return 32 * EMBP; }
   __host__ __device__ static constexpr int off_Wh(int i) { return 2 * 32 * EMBP + (i - 1) * 1024; }   // i = 1..4
-  __host__ __device__ static constexpr int off_Wc(int i) { return 2 * 32 * EMBP + 4 * 1024 + i * 32 * CD; }
-  __host__ __device__ static constexpr int TOT() { return 2 * 32 * EMBP + 4 * 1024 + 5 * 32 * CD; }
+  __host__ __device__ static constexpr int off_M(int i) { return 2 * 32 * EMBP + 4 * 1024 + i * 32 * CD; }   // i = 0..3
+  __host__ __device__ static constexpr int TOT() { return 2 * 32 * EMBP + 4 * 1024 + 4 * 32 * CD; }
   __host__ __device__ static constexpr int off_B() { return 2 * TOT(); }
   __host__ __device__ static constexpr int off_b(int i) { return off_B() + 3 * EMBP + 32 * i; }
-  __host__ __device__ static constexpr int off_bc(int i) { return off_B() + 3 * EMBP + 160 + 32 * i; }
-  __host__ __device__ static constexpr int off_Wo() { return off_B() + 3 * EMBP + 320; }
-  __host__ __device__ static constexpr int off_bo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int off_Wo() { return off_B() + 3 * EMBP + 160; }
+  __host__ __device__ static constexpr int off_Mo() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int off_bo() { return off_Mo() + 4 * CD; }
   __host__ __device__ static constexpr int total() { return off_bo() + 4; }
 };
 __host__ __device__ constexpr int canon_off(int n, int k, int K) { return (n / 8) * (K / 4) * 32 + (k / 4) * 32 + (n % 8) * 4 + (k % 4); }

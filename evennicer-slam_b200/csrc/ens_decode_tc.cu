@@ -11,9 +11,11 @@
 //   * trilinear gather of its 32 (64) features, split hi/lo, tcgen05.st into the feature columns (A operand in TMEM);
 //   * Fourier embedding in three 32-column chunks: sin -> hi/lo -> tcgen05.st; one elected thread issues
 //     D  += e W0^T  and  D3 += e W3e^T  (3xTF32: lo.hi, hi.lo, hi.hi; M = 128 points, N = 32, K = 8 per instruction);
-//   * per block i: tcgen05.ld of D (W_i x) and Dc (Wc_i c); h = relu(D + b_i) + Dc + bc_i in registers; hi/lo -> x
-//     columns; next block's hidden GEMM (into D, or into D3 for the skip block) and feature GEMM are issued;
-//   * output layer on the FMA pipe (32 x NO), read-modify-write of the output row.
+//   * per block i: tcgen05.ld of the accumulator; r = relu(D + b'_i) in registers; hi/lo -> x columns; the next
+//     block's hidden GEMM and its folded feature GEMM (M_i = W_{i+1} Wc_i, see MlpPackTC) accumulate into D (or D3 for
+//     the skip block);
+//   * output layer on the FMA pipe (Wo r_4 + Mo c + bo'), read-modify-write of the output row.
+// Two tiles are in flight per CTA (two groups of four warps with their own TMEM columns and barriers).
 // Completion of each MMA batch is tracked with tcgen05.commit -> mbarrier; thread sync around TMEM stores uses
 // tcgen05.wait::st + tcgen05.fence + bar.sync.  Verified first in isolation by scratch/tc_probe.cu.
 #include "ens_mma.cuh"
@@ -139,32 +141,40 @@ struct TcArgs {
   int apply_mask;         // last launch of the stage and the caller wants the bound rule
 };
 
-// TMEM columns (one 128-point tile in flight)
-constexpr int TC_D = 0, TC_D3 = 32, TC_DC = 64, TC_EH = 96, TC_EL = 128, TC_XH = 160, TC_XL = 192, TC_FH = 224, TC_FL = 288;
-constexpr int TC_COLS = 512;
+// Two 128-point tiles are in flight per CTA: tile group 0 = warps 0-3, group 1 = warps 4-7; each owns 256 TMEM columns,
+// an mbarrier and a named barrier, and walks its own tile sequence, so one group's epilogue overlaps the other's MMAs.
+// TMEM columns of a group: accumulators D and D3 (the skip block's, which starts with W3e e), the A operands
+// e-chunk / x (hi, lo) and the features (hi, lo; CD columns each).
+constexpr int TC_D = 0, TC_D3 = 32, TC_XH = 64, TC_XL = 96, TC_FH = 128;
+constexpr int TC_GROUP_COLS = 256, TC_COLS = 512;
+
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory"); }
 
 template <int LEVEL, int CD, int NO, bool F64>
-__global__ void __launch_bounds__(128, 1) decode_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
   using P = MlpPackTC<CD>;
+  constexpr int TC_FL = TC_FH + CD;
+  static_assert(TC_FL + CD <= TC_GROUP_COLS, "TMEM budget of a tile group");
   extern __shared__ __align__(128) float smem[];
   float *sw = smem;                                     // the tc blob
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, gwarp = (tid >> 5) & 3;
 
   {   // stage the blob once per CTA
     const float *gw = a.sc.w[LEVEL] + off_tc<CD>();
     const uint32_t s0 = smem_u32(sw);
-    for (int i = tid; i < P::total() / 4; i += 128)
+    for (int i = tid; i < P::total() / 4; i += 256)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if ((tid >> 5) == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TC_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -172,14 +182,15 @@ __global__ void __launch_bounds__(128, 1) decode_tc_kernel(TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = tmem_base_s + ((uint32_t)(32 * warp) << 16);      // this warp's lane quarter
-  const uint32_t tb0 = tmem_base_s;                                     // MMA operands address lane 0
+  const uint32_t tb0 = tmem_base_s + (uint32_t)(TC_GROUP_COLS * grp);   // MMA operands address lane 0
+  const uint32_t tb = tb0 + ((uint32_t)(32 * gwarp) << 16);             // this warp's lane quarter
   const uint32_t swb = smem_u32(sw);
+  uint64_t *bar = &bars[grp];
   uint32_t parity = 0;
 
   const int64_t n_tiles = (a.n + 127) / 128;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t pt = tile * 128 + tid;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+    const int64_t pt = tile * 128 + gt;
     const bool valid = pt < a.n;
     float pn[3], p32[3];
     bool inside = true;
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(128, 1) decode_tc_kernel(TcArgs a) {
         inside &= (p32[k] < __double2float_rn(a.sc.hi[k])) && (p32[k] > __double2float_rn(a.sc.lo[k]));
     }
 
-    // ---- features -> TMEM (A operand of the five fc_c GEMMs) ----
+    // ---- features -> TMEM (A operand of the folded feature GEMMs; read back for the output layer) ----
     {
       float f[32];
       gather_regs(a.sc.grid[LEVEL], a.sc.dims[LEVEL], pn, f);
@@ -218,74 +229,83 @@ __global__ void __launch_bounds__(128, 1) decode_tc_kernel(TcArgs a) {
         const float q = fmaf(p32[2], B[2 * EMBP + k], fmaf(p32[1], B[EMBP + k], p32[0] * B[k]));
         e[k] = fast_sin(q);
       }
-      if (jc > 0) { mbar_wait(&bar, parity); parity ^= 1; tc_fence_after(); }     // previous chunk consumed
-      tmem_st32_split(tb + TC_EH, tb + TC_EL, e);
+      if (jc > 0) { mbar_wait(bar, parity); parity ^= 1; tc_fence_after(); }     // previous chunk consumed
+      tmem_st32_split(tb + TC_XH, tb + TC_XL, e);
       tmem_st_done();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
+      group_sync(grp);
+      if (gt == 0) {
         tc_fence_after();
-        // chunk jc = columns 32jc..32jc+31 of the [32][96] matrices = k-steps 4jc..4jc+3: +8 core matrices = +1024 B
-        issue_gemm<32, EMBP>(tb0 + TC_D, tb0 + TC_EH, tb0 + TC_EL, swb + jc * 1024, P::off_W0(), P::TOT(), jc > 0);
-        issue_gemm<32, EMBP>(tb0 + TC_D3, tb0 + TC_EH, tb0 + TC_EL, swb + jc * 1024, P::off_W3e(), P::TOT(), jc > 0);
-        if (jc == 2) issue_gemm<CD, CD>(tb0 + TC_DC, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_Wc(0), P::TOT(), 0);   // Wc_0 c
-        umma_commit(&bar);
+        // chunk jc = columns 32jc..32jc+31 of the [32][96] matrices = +8 core matrices = +1024 B
+        issue_gemm<32, EMBP>(tb0 + TC_D, tb0 + TC_XH, tb0 + TC_XL, swb + jc * 1024, P::off_W0(), P::TOT(), jc > 0);
+        issue_gemm<32, EMBP>(tb0 + TC_D3, tb0 + TC_XH, tb0 + TC_XL, swb + jc * 1024, P::off_W3e(), P::TOT(), jc > 0);
+        umma_commit(bar);
       }
     }
-    // ---- blocks 0..4 ----
-    float h[32];
+    // ---- blocks 0..4:  r_i = relu(u_i + b'_i);  u_{i+1} = W_{i+1} r_i + M_i c ----
+    float r[32];
 #pragma unroll 1
     for (int i = 0; i < 5; ++i) {
-      mbar_wait(&bar, parity); parity ^= 1;
+      mbar_wait(bar, parity); parity ^= 1;
       tc_fence_after();
-      float u[32], c[32];
-      tmem_ld32(tb + (i == 3 ? TC_D3 : TC_D), u);
-      tmem_ld32(tb + TC_DC, c);
-      const float *bi = sw + P::off_b(0) + 32 * i, *bci = sw + P::off_bc(0) + 32 * i;
+      tmem_ld32(tb + (i == 3 ? TC_D3 : TC_D), r);
+      const float *bi = sw + P::off_b(0) + 32 * i;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) h[k] = fmaxf(u[k] + bi[k], 0.f) + (c[k] + bci[k]);
+      for (int k = 0; k < 32; ++k) r[k] = fmaxf(r[k] + bi[k], 0.f);
       if (i < 4) {
-        tmem_st32_split(tb + TC_XH, tb + TC_XL, h);
+        tmem_st32_split(tb + TC_XH, tb + TC_XL, r);
         tmem_st_done();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp);
+        if (gt == 0) {
           tc_fence_after();
-          // next block's hidden GEMM: into D3 (which already holds W3e e) for the skip block, else overwrite D
-          if (i + 1 == 3) issue_gemm<32, 32>(tb0 + TC_D3, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(3), P::TOT(), 1);
-          else issue_gemm<32, 32>(tb0 + TC_D, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(1) + i * 1024, P::TOT(), 0);
-          issue_gemm<CD, CD>(tb0 + TC_DC, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_Wc(0) + (i + 1) * 32 * CD, P::TOT(), 0);
-          umma_commit(&bar);
+          const uint32_t dst = tb0 + ((i + 1 == 3) ? TC_D3 : TC_D);      // the skip block continues D3 (= W3e e)
+          issue_gemm<32, 32>(dst, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(1) + i * 1024, P::TOT(), (i + 1 == 3) ? 1u : 0u);
+          issue_gemm<CD, CD>(dst, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_M(0) + i * 32 * CD, P::TOT(), 1u);
+          umma_commit(bar);
         }
       }
     }
-    // ---- output layer (FMA pipe), read-modify-write of the output row ----
+    // ---- output layer (FMA pipe): out = Wo r_4 + Mo c + bo' ----
     float o[NO];
 #pragma unroll
     for (int q = 0; q < NO; ++q) {
       const float *Wo = sw + P::off_Wo() + 32 * q;
       float s = sw[P::off_bo() + q];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) s = fmaf(Wo[k], h[k], s);
+      for (int k = 0; k < 32; ++k) s = fmaf(Wo[k], r[k], s);
       o[q] = s;
+    }
+#pragma unroll
+    for (int half = 0; half < CD / 32; ++half) {
+      float c[32];
+      tmem_ld32(tb + TC_FH + 32 * half, c);                 // the hi columns hold the features themselves
+#pragma unroll
+      for (int q = 0; q < NO; ++q) {
+        const float *Mo = sw + P::off_Mo() + CD * q + 32 * half;
+        float s = o[q];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s = fmaf(Mo[k], c[k], s);
+        o[q] = s;
+      }
     }
     if (valid) {
       float4 *dst = reinterpret_cast<float4 *>(a.out4) + pt;
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (LEVEL == ENS_LEVEL_MIDDLE) r.w = o[0];
-      else if (LEVEL == ENS_LEVEL_FINE) { r = *dst; r.w = __fadd_rn(o[0], r.w); }
-      else { r = *dst; r.x = o[0]; r.y = o[1]; r.z = o[2]; }
-      if (a.apply_mask && !inside) r.w = 100.f;
-      *dst = r;
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LEVEL == ENS_LEVEL_MIDDLE) v4.w = o[0];
+      else if (LEVEL == ENS_LEVEL_FINE) { v4 = *dst; v4.w = __fadd_rn(o[0], v4.w); }
+      else { v4 = *dst; v4.x = o[0]; v4.y = o[1]; v4.z = o[2]; }
+      if (a.apply_mask && !inside) v4.w = 100.f;
+      *dst = v4;
     }
-    // the next tile's first tcgen05.st must not overtake this tile's TMEM loads
+    // the next tile's tcgen05.st must not overtake this tile's TMEM loads
     tc_fence_before();
-    __syncthreads();
+    group_sync(grp);
     tc_fence_after();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"((uint32_t)TC_COLS) : "memory");
+  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"((uint32_t)TC_COLS) : "memory");
 }
 
 template <int LEVEL, int CD, int NO>
@@ -296,14 +316,14 @@ static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = (n + 127) / 128;
-  const unsigned g = (unsigned)(tiles < sms ? tiles : sms);
+  const int64_t pairs = ((n + 127) / 128 + 1) / 2;
+  const unsigned g = (unsigned)(pairs < sms ? pairs : sms);
   if (f64) {
     if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
-    decode_tc_kernel<LEVEL, CD, NO, true><<<g, 128, smem, s>>>(a);
+    decode_tc_kernel<LEVEL, CD, NO, true><<<g, 256, smem, s>>>(a);
   } else {
     if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
-    decode_tc_kernel<LEVEL, CD, NO, false><<<g, 128, smem, s>>>(a);
+    decode_tc_kernel<LEVEL, CD, NO, false><<<g, 256, smem, s>>>(a);
   }
   ENS_CHECK_CUDA();
   return ENS_OK;

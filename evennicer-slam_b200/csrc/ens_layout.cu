@@ -167,37 +167,58 @@ __device__ __forceinline__ void pack_mlp_v2b_body(const PtrTable &t, float *__re
   out[idx] = v;
 }
 
-// tcgen05 layout (see MlpPackTC): canonical UMMA K-major core matrices, value and tf32 remainder
+// tcgen05 layout (see MlpPackTC): canonical UMMA K-major core matrices, value and tf32 remainder; the feature
+// matrices are pre-multiplied into the next block (float64 accumulation, rounded once)
 template <int CD, int NO>
 __device__ __forceinline__ void pack_mlp_tc_body(const PtrTable &t, float *__restrict__ out, int idx) {
   using P = MlpPackTC<CD>;
+  // hidden part of pts_linears[i].weight, i = 1..4
+  auto Wh = [&](int i, int n, int j) { return (i == 3) ? t.p[11 + 2 * 3][n * 125 + EMB + j] : t.p[11 + 2 * i][n * 32 + j]; };
   float v = 0.f;
   if (idx < 2 * P::TOT()) {
     const bool lo = idx >= P::TOT();
     int o = lo ? idx - P::TOT() : idx;
-    // which matrix
     int K, mat, i = 0;
     if (o < P::off_W3e()) { mat = 0; K = EMBP; }
     else if (o < P::off_Wh(1)) { mat = 1; K = EMBP; o -= P::off_W3e(); }
-    else if (o < P::off_Wc(0)) { mat = 2; K = 32; o -= P::off_Wh(1); i = 1 + o / 1024; o %= 1024; }
-    else { mat = 3; K = CD; o -= P::off_Wc(0); i = o / (32 * CD); o %= (32 * CD); }
+    else if (o < P::off_M(0)) { mat = 2; K = 32; o -= P::off_Wh(1); i = 1 + o / 1024; o %= 1024; }
+    else { mat = 3; K = CD; o -= P::off_M(0); i = o / (32 * CD); o %= (32 * CD); }
     const int ni = o / ((K / 4) * 32), r1 = o % ((K / 4) * 32);
     const int ki = r1 / 32, r2 = r1 % 32;
     const int n = ni * 8 + r2 / 4, k = ki * 4 + r2 % 4;
     float w = 0.f;
     if (mat == 0) w = (k < EMB) ? t.p[11][n * EMB + k] : 0.f;
     else if (mat == 1) w = (k < EMB) ? t.p[11 + 2 * 3][n * 125 + k] : 0.f;
-    else if (mat == 2) w = (i == 3) ? t.p[11 + 2 * 3][n * 125 + EMB + k] : t.p[11 + 2 * i][n * 32 + k];
-    else w = t.p[2 * i][n * CD + k];
+    else if (mat == 2) w = Wh(i, n, k);
+    else {                                       // M_i[n][k] = sum_j Wh_{i+1}[n][j] Wc_i[j][k]
+      double acc = 0.0;
+      for (int j = 0; j < 32; ++j) acc += (double)Wh(i + 1, n, j) * (double)t.p[2 * i][j * CD + k];
+      w = (float)acc;
+    }
     const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
     v = lo ? (w - hi) : w;
   } else {
     int o = idx - P::off_B();
     if (o < 3 * EMBP) { int r = o / EMBP, k = o % EMBP; v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f; }
-    else if (o < 3 * EMBP + 160) { o -= 3 * EMBP; v = t.p[12 + 2 * (o / 32)][o % 32]; }
-    else if (o < 3 * EMBP + 320) { o -= 3 * EMBP + 160; v = t.p[2 * (o / 32) + 1][o % 32]; }
-    else if (o < 3 * EMBP + 320 + 128) { o -= 3 * EMBP + 320; int n = o / 32, j = o % 32; v = (n < NO) ? t.p[21][n * 32 + j] : 0.f; }
-    else { int n = o - (3 * EMBP + 320 + 128); v = (n < NO) ? t.p[22][n] : 0.f; }
+    else if (o < 3 * EMBP + 160) {               // b'_i
+      o -= 3 * EMBP;
+      const int i = o / 32, n = o % 32;
+      double acc = (double)t.p[12 + 2 * i][n];
+      if (i > 0) for (int j = 0; j < 32; ++j) acc += (double)Wh(i, n, j) * (double)t.p[2 * (i - 1) + 1][j];
+      v = (float)acc;
+    } else if (o < 3 * EMBP + 160 + 128) { o -= 3 * EMBP + 160; int n = o / 32, j = o % 32; v = (n < NO) ? t.p[21][n * 32 + j] : 0.f; }
+    else if (o < 3 * EMBP + 160 + 128 + 4 * CD) {   // Mo[q][k] = sum_j Wo[q][j] Wc_4[j][k]
+      o -= 3 * EMBP + 160 + 128;
+      const int q = o / CD, k = o % CD;
+      double acc = 0.0;
+      if (q < NO) for (int j = 0; j < 32; ++j) acc += (double)t.p[21][q * 32 + j] * (double)t.p[2 * 4][j * CD + k];
+      v = (float)acc;
+    } else {                                     // bo'[q] = bo[q] + sum_j Wo[q][j] bc_4[j]
+      const int q = o - (3 * EMBP + 160 + 128 + 4 * CD);
+      double acc = 0.0;
+      if (q < NO) { acc = (double)t.p[22][q]; for (int j = 0; j < 32; ++j) acc += (double)t.p[21][q * 32 + j] * (double)t.p[2 * 4 + 1][j]; }
+      v = (float)acc;
+    }
   }
   out[idx] = v;
 }

@@ -905,8 +905,9 @@ extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts
   const DevScene sc = make_dev_scene(scene);
   cudaStream_t s = (cudaStream_t)stream;
   {
-    const char *v = std::getenv("ENS_EVAL_VARIANT");          // "tc" (tcgen05) | "mma" | "fma"
-    if (v && std::strcmp(v, "tc") == 0) {
+    // variant of the forward-only decode: "tc" (tcgen05 / TMEM, default) | "mma" (mma.sync) | ENS_FWD_VARIANT=fma
+    const char *v = std::getenv("ENS_EVAL_VARIANT");
+    if (!(v && std::strcmp(v, "mma") == 0) && use_mma_forward()) {
       rc = tc_eval_points(sc, stage, pts, pts_is_f64, n, apply_bound_mask, out4, s);
       if (rc != ENS_EUNSUPPORTED) return rc;
     }

@@ -35,7 +35,7 @@ def test_library_loads_and_reports_version():
     from evennicer_slam_b200 import _lib
     L = _lib.lib()
     assert L.ens_version() == 2
-    assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 + 41700 and L.ens_decoder_grad_floats(3) == 15899
+    assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 + 37700 and L.ens_decoder_grad_floats(3) == 15899
 
 
 def test_grid_layout_roundtrip():
@@ -123,9 +123,15 @@ def test_eval_points(tiny, stage):
 
 
 @pytest.mark.parametrize("stage", ["middle", "fine", "color"])
-def test_eval_points_tcgen05_variant(tiny, stage, monkeypatch):
-    """The tcgen05/TMEM decode (ens_decode_tc.cu; opt-in with ENS_EVAL_VARIANT=tc) against the reference goldens."""
-    monkeypatch.setenv("ENS_EVAL_VARIANT", "tc")
+def test_eval_points_variants(tiny, stage, monkeypatch):
+    """Both forward-only decode variants against the reference goldens: the tcgen05/TMEM kernels (ens_decode_tc.cu,
+    default) and the mma.sync kernels (ENS_EVAL_VARIANT=mma)."""
+    for variant in ("tc", "mma"):
+        monkeypatch.setenv("ENS_EVAL_VARIANT", variant)
+        _check_eval_variant(tiny, stage)
+
+
+def _check_eval_variant(tiny, stage):
     scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
     g = load_golden("tiny_eval_points.npz")
     pts = cases.eval_points_lattice(scene)
