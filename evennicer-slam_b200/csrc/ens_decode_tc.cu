@@ -340,4 +340,90 @@ int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f6
   return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Renderer.render_batch_ray forward WITHOUT a backward (render_img, visualisation, mesh colours) on the tcgen05 decode:
+//   place_kernel      sample placement (float64, same code as the fused kernels) -> z [R][S], points [R*S][3] f64
+//   decode_tc_kernel  one launch per decoder, bound rule included               -> raw [R][S][4]
+//   composite_kernel  raw2outputs_nerf_color (common.py:256-297), one thread per ray, the reference's sequential order
+// The three per-point arrays live in a caller-provided scratch (ens_fwd_scratch_bytes).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT_MMA) place_kernel(DevScene sc, RayArgs ra, double *__restrict__ z_out,
+                                                       double *__restrict__ pts) {
+  __shared__ double zc[NT_MMA], zs[NT_MMA];
+  const int S = ra.S;
+  const int rl = threadIdx.x / S, s = threadIdx.x % S;
+  const int64_t ray = (int64_t)blockIdx.x * ra.rpc + rl;
+  const bool valid = (rl < ra.rpc) && (ray < ra.R);
+  float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = ra.rays_o[ray * 3 + k]; d[k] = ra.rays_d[ray * 3 + k]; }
+  }
+  const double z = place_sample(ra, sc, valid, ray, rl, s, o, d, zc, zs);
+  if (valid) {
+    const int64_t pi = ray * S + s;
+    z_out[pi] = z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pts[pi * 3 + k] = __dadd_rn((double)o[k], __dmul_rn((double)d[k], z));   // Renderer.py:173-174
+  }
+}
+
+__global__ void __launch_bounds__(128) composite_kernel(const float4 *__restrict__ raw, const double *__restrict__ z,
+                                                        int64_t R, int S, double *__restrict__ depth,
+                                                        double *__restrict__ var, float *__restrict__ color,
+                                                        float *__restrict__ w_out) {
+  const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= R) return;
+  const float4 *rr = raw + ray * S;
+  const double *zz = z + ray * S;
+  float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
+  double dep = 0.0;
+  for (int k = 0; k < S; ++k) {                       // sequential cumprod / sums, exactly the fused kernels' order
+    const float4 rk = rr[k];
+    const float alpha = 1.f / (1.f + expf(-(10.f * rk.w)));
+    const float wk = __fmul_rn(alpha, T);
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+    dep = __dadd_rn(dep, __dmul_rn((double)wk, zz[k]));
+    cr = __fadd_rn(cr, __fmul_rn(wk, rk.x)); cg = __fadd_rn(cg, __fmul_rn(wk, rk.y)); cb = __fadd_rn(cb, __fmul_rn(wk, rk.z));
+    if (w_out) w_out[ray * S + k] = wk;
+  }
+  double v = 0.0;
+  T = 1.f;
+  for (int k = 0; k < S; ++k) {
+    const float alpha = 1.f / (1.f + expf(-(10.f * rr[k].w)));
+    const float wk = __fmul_rn(alpha, T);
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+    const double tmp = __dsub_rn(zz[k], dep);
+    v = __dadd_rn(v, __dmul_rn(__dmul_rn((double)wk, tmp), tmp));
+  }
+  depth[ray] = dep;
+  var[ray] = v;
+  color[ray * 3 + 0] = cr; color[ray * 3 + 1] = cg; color[ray * 3 + 2] = cb;
+}
+
+int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage) {
+  if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
+  return n_rays * (int64_t)S * (24 + 8 + 16);
+}
+
+int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s) {
+  if (stage == ENS_STAGE_COARSE) return ENS_EUNSUPPORTED;
+  const int64_t P = a.ra.R * (int64_t)a.ra.S;
+  if (!scratch || scratch_bytes < tc_fwd_scratch_bytes(a.ra.R, a.ra.S, stage)) return ENS_EUNSUPPORTED;
+  char *base = reinterpret_cast<char *>(scratch);
+  double *pts = reinterpret_cast<double *>(base);
+  double *z = a.z_out ? a.z_out : reinterpret_cast<double *>(base + P * 24);
+  float *raw = a.raw_out ? a.raw_out : reinterpret_cast<float *>(base + P * 32);
+  a.ra.rpc = NT_MMA / a.ra.S;
+  const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
+  place_kernel<<<g, NT_MMA, 0, s>>>(a.sc, a.ra, z, pts);
+  ENS_CHECK_CUDA();
+  const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s);
+  if (rc != ENS_OK) return rc;
+  composite_kernel<<<(unsigned)((a.ra.R + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4 *>(raw), z, a.ra.R, a.ra.S,
+                                                                    a.depth, a.var, a.color, a.w_out);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
 }  // namespace ens

@@ -271,6 +271,8 @@ int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s);
 // tcgen05 variant (ens_decode_tc.cu)
 int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
                    float *out4, cudaStream_t s);
+int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s);
+int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage);
 int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset);
 int mma_render_bwd(BwdArgs &a, int stage, bool wg, cudaStream_t s);
 int64_t mma_bwd_workspace_bytes(int64_t n_rays, int S);

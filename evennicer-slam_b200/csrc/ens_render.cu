@@ -928,7 +928,8 @@ extern "C" int ens_eval_points(const EnsScene *scene, int stage, const void *pts
 extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                               const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                               double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,
-                              void *saved, int64_t saved_bytes, int saved_with_activations, ens_stream_t stream) {
+                              void *saved, int64_t saved_bytes, int saved_with_activations, void *scratch,
+                              int64_t scratch_bytes, ens_stream_t stream) {
   int rc = check_scene(scene, stage);
   if (rc != ENS_OK) return rc;
   if (n_rays < 0) return ENS_EINVAL;
@@ -956,6 +957,14 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
     }
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (use_mma_forward() && a.save_masks == nullptr && scratch != nullptr) {
+    // no backward will follow and the caller gave scratch: placement + tcgen05 decode + compositing
+    const char *v = std::getenv("ENS_EVAL_VARIANT");
+    if (!(v && std::strcmp(v, "mma") == 0)) {
+      rc = tc_render_fwd(a, stage, scratch, scratch_bytes, s);
+      if (rc != ENS_EUNSUPPORTED) return rc;
+    }
+  }
   if (use_mma_forward()) {
     rc = mma_render_fwd(a, stage, s);
     if (rc != ENS_EUNSUPPORTED) return rc;       // coarse stage: fma kernels below
@@ -971,6 +980,11 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
 extern "C" int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int stage, int want_decoder_grads) {
   if (!use_mma_forward() || !use_mma_backward()) return 0;
   return mma_fwd_saved_bytes(n_rays, n_samples_total, stage, want_decoder_grads, nullptr, nullptr);
+}
+
+extern "C" int64_t ens_fwd_scratch_bytes(int64_t n_rays, int n_samples_total, int stage) {
+  if (!use_mma_forward()) return 0;
+  return tc_fwd_scratch_bytes(n_rays, n_samples_total, stage);
 }
 
 extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads) {

@@ -15,6 +15,8 @@ from ._lib import LEVELS, STAGES, STAGE_LEVELS, EnsGrads, EnsRenderCfg
 from .scene import SceneCache, build_scene_struct, decoder_grad_views, is_native_strided
 
 
+TC_MIN_POINTS = 1         # every forward-only call takes the placement + tcgen05 decode + compositing path (one variant for all
+                          # batch sizes keeps the forward bit-independent of how a frame is cut into batches)
 SAVE_FORWARD = True    # keep relu masks / activations from the forward kernel for the backward (False: it recomputes)
 _DEBUG: Dict[str, object] = {}     # test hook: set _DEBUG["keep_workspace"]=True to inspect the backward scratch
 
@@ -146,12 +148,19 @@ class _RenderBatchRay(torch.autograd.Function):
             nbytes = int(L.ens_fwd_saved_bytes(R, S, STAGES[setup.stage], int(want_dec)))
             if nbytes > 0:
                 saved = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
+        scratch = None
+        if saved is None and not want_bwd and R * S >= TC_MIN_POINTS:
+            # forward only (render_img, visualisation) and a large batch: scratch for the three-kernel tcgen05 path
+            nbytes = int(L.ens_fwd_scratch_bytes(R, S, STAGES[setup.stage]))
+            if nbytes > 0:
+                scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
         stream = _lib.cur_stream(dev)
         _lib.check(TIMER.launch("render_fwd", dev, lambda: L.ens_render_fwd(
             C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd),
             _lib.ptr(depth_max) if has_depth else None, R, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color),
             _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0,
-            int(want_dec), stream)), "ens_render_fwd")
+            int(want_dec), _lib.ptr(scratch), scratch.numel() * 8 if scratch is not None else 0,
+            stream)), "ens_render_fwd")
         ctx.saved_fwd = saved
         ctx.saved_has_h = bool(want_dec)
         ctx.grid_native_strided = [is_native_strided(g) for g in grids]

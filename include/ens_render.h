@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ENS_ABI_VERSION 2
+#define ENS_ABI_VERSION 3
 
 typedef void *ens_stream_t; /* cudaStream_t */
 
@@ -101,6 +101,10 @@ int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_de
  * decoder gradients will be wanted) so that ens_render_bwd does not recompute the forward -- what torch autograd
  * keeps as saved tensors in the reference.  0 = not applicable for this stage / sample count (pass NULL). */
 int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int stage, int want_decoder_grads);
+/* bytes of optional scratch for a forward that will NOT be followed by a backward (render_img, visualisation): with it
+ * ens_render_fwd runs sample placement, the tcgen05 decode and the compositing as separate kernels over per-point
+ * arrays in this scratch (faster for large batches); without it the fused kernel is used.  0 = not applicable. */
+int64_t ens_fwd_scratch_bytes(int64_t n_rays, int n_samples_total, int stage);
 
 /* [32][Z][Y][X] -> [Z][Y][X][32]  and back.  n_vox = Z*Y*X.  (layout of `c`, EvenNICER_SLAM.py:217-275) */
 int ens_grid_to_native(const float *ref_layout, float *native, int64_t n_vox, ens_stream_t stream);
@@ -158,11 +162,13 @@ int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_i
  * Outputs: depth f64 [R], var f64 [R], color f32 [R][3].  Optional (may be NULL): z_vals f64 [R][S],
  * weights f32 [R][S], raw f32 [R][S][4] (pre-sigmoid; `raw` is also what ens_render_bwd wants back).
  * saved / saved_bytes: optional buffer of ens_fwd_saved_bytes(n_rays, S, stage, saved_with_activations) bytes,
- * filled for ens_render_bwd (16-byte aligned; NULL = the backward recomputes). */
+ * filled for ens_render_bwd (16-byte aligned; NULL = the backward recomputes).
+ * scratch / scratch_bytes: optional, see ens_fwd_scratch_bytes (only used when saved is NULL). */
 int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                    const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                    double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,
-                   void *saved, int64_t saved_bytes, int saved_with_activations, ens_stream_t stream);
+                   void *saved, int64_t saved_bytes, int saved_with_activations, void *scratch,
+                   int64_t scratch_bytes, ens_stream_t stream);
 
 /* Backward of ens_render_fwd into grid features, decoder weights and rays.
  * Recomputes sample placement and activations; `raw` is the [R][S][4] tensor saved by the forward.
