@@ -33,15 +33,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell)
   return d;
 }
-// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, N = 32, K = 8
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, K = 8, N from the instruction descriptor.  Executed by a
+// whole (converged) warp with identical operands; elect.sync picks the one lane that issues, so the surrounding code
+// stays warp-uniform (no per-instruction broadcast loops out of a divergent branch).
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
       :: "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
@@ -113,24 +117,28 @@ __device__ __forceinline__ void gather_regs(const float *__restrict__ grid, cons
   }
 }
 
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: f32 accumulate, TF32 x TF32, both K-major, N columns, M = 128
+__host__ __device__ constexpr uint32_t tc_idesc(int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 // issue  D (+)= A[128 x K] * W[32 x K]^T  in 3xTF32; A: hi at a_hi, lo at a_lo (TMEM columns), W: canonical smem
 // matrix at float offset w_off (value) and w_off + TOT (remainder).  first_acc: 0 = overwrite D with the first MMA.
-template <int K, int KMAT>
+template <int K, int KMAT, int N = 32>
 __device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t sw_base, int w_off, int tot,
                                            uint32_t first_acc) {
-  // K columns of a [32][KMAT] canonical matrix starting at float offset w_off (a column offset of 4c inside the
+  // K columns of a [N][KMAT] canonical matrix starting at float offset w_off (a column offset of 4c inside the
   // matrix is c*128 bytes and is folded into sw_base by the caller); SBO is that of the WHOLE matrix
   const uint64_t dh = umma_desc(sw_base + (uint32_t)w_off * 4u, (KMAT / 4) * 128u);
   const uint64_t dl = umma_desc(sw_base + (uint32_t)(w_off + tot) * 4u, (KMAT / 4) * 128u);
+  constexpr uint32_t IDESC = tc_idesc(N);
   uint32_t acc = first_acc;
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) { umma_ts(d, a_lo + 8 * ks, dh + (uint64_t)(16 * ks), TC_IDESC, acc); acc = 1; }
+  for (int ks = 0; ks < K / 8; ++ks) { umma_ts(d, a_lo + 8 * ks, dh + (uint64_t)(16 * ks), IDESC, acc); acc = 1; }
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dl + (uint64_t)(16 * ks), TC_IDESC, 1);
+  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dl + (uint64_t)(16 * ks), IDESC, 1);
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dh + (uint64_t)(16 * ks), TC_IDESC, 1);
+  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dh + (uint64_t)(16 * ks), IDESC, 1);
 }
 
 struct TcArgs {
@@ -155,6 +163,7 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
   using P = MlpPackTC<CD>;
   constexpr int TC_FL = TC_FH + CD;
   static_assert(TC_FL + CD <= TC_GROUP_COLS, "TMEM budget of a tile group");
+  static_assert(P::off_W3e() == P::off_W0() + 32 * EMBP && TC_D3 == TC_D + 32, "[W0; W3e] and [D | D3] must be contiguous");
   extern __shared__ __align__(128) float smem[];
   float *sw = smem;                                     // the tc blob
   __shared__ __align__(8) uint64_t bars[2];
@@ -234,12 +243,14 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
       tmem_st_done();
       tc_fence_before();
       group_sync(grp);
-      if (gt == 0) {
+      if (gwarp == 0) {
         tc_fence_after();
-        // chunk jc = columns 32jc..32jc+31 of the [32][96] matrices = +8 core matrices = +1024 B
-        issue_gemm<32, EMBP>(tb0 + TC_D, tb0 + TC_XH, tb0 + TC_XL, swb + jc * 1024, P::off_W0(), P::TOT(), jc > 0);
-        issue_gemm<32, EMBP>(tb0 + TC_D3, tb0 + TC_XH, tb0 + TC_XL, swb + jc * 1024, P::off_W3e(), P::TOT(), jc > 0);
+        // chunk jc = columns 32jc..32jc+31 of the matrices = +8 core matrices = +1024 B.  W3e follows W0 in the blob at
+        // exactly four 8-row groups, so [W0; W3e] is ONE canonical [64][96] matrix and [D | D3] (adjacent TMEM
+        // columns) one N = 64 accumulator: a single GEMM feeds both.
+        issue_gemm<32, EMBP, 64>(tb0 + TC_D, tb0 + TC_XH, tb0 + TC_XL, swb + jc * 1024, P::off_W0(), P::TOT(), jc > 0);
         umma_commit(bar);
+        __syncwarp();
       }
     }
     // ---- blocks 0..4:  r_i = relu(u_i + b'_i);  u_{i+1} = W_{i+1} r_i + M_i c ----
@@ -257,12 +268,13 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
         tmem_st_done();
         tc_fence_before();
         group_sync(grp);
-        if (gt == 0) {
+        if (gwarp == 0) {
           tc_fence_after();
           const uint32_t dst = tb0 + ((i + 1 == 3) ? TC_D3 : TC_D);      // the skip block continues D3 (= W3e e)
           issue_gemm<32, 32>(dst, tb0 + TC_XH, tb0 + TC_XL, swb, P::off_Wh(1) + i * 1024, P::TOT(), (i + 1 == 3) ? 1u : 0u);
           issue_gemm<CD, CD>(dst, tb0 + TC_FH, tb0 + TC_FL, swb, P::off_M(0) + i * 32 * CD, P::TOT(), 1u);
           umma_commit(bar);
+          __syncwarp();
         }
       }
     }
