@@ -605,13 +605,14 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
     out = {}
 
     def timed(fn, reps):
-        fn(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        """median CUDA-event time of `reps` calls after two warm-up calls (lazy module loads, allocator growth)"""
+        fn(); fn(); torch.cuda.synchronize()
+        ts = []
         for _ in range(reps):
-            fn()
-        b.record(); torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
 
     ct = torch.from_numpy(cam_t.copy()).to(dev).requires_grad_(True)
 
@@ -629,7 +630,7 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
 
     def full_frame():
         renderer.render_img(c, decoders, c2w, dev, "color", gt_depth=depth_t)
-    ms = timed(full_frame, 2)
+    ms = timed(full_frame, 3)
     n = cam.H * cam.W
     out["full_frame"] = {"rays": n, "ms": ms, "rays_per_s": n / ms * 1e3,
                          "frac_of_hbm_roofline": n / ms * 1e3 * 147456 / (hbm_peak()[0] * 1e9)}
@@ -645,7 +646,7 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
             idx = torch.arange(lo, min(total, lo + chunk * 8), device=dev)
             pts = torch.stack([lin[0][idx % 256], lin[1][(idx // 256) % 256], lin[2][idx // 65536]], -1)
             renderer.eval_points(pts, decoders, c, "fine", dev)
-    ms = timed(mesh, 1)
+    ms = timed(mesh, 3)
     n = 256 ** 3
     out["mesh_lattice"] = {"points": n, "ms": ms, "points_per_s": n / ms * 1e3,
                            "frac_of_hbm_roofline": n / ms * 1e3 * 2048 / (hbm_peak()[0] * 1e9)}

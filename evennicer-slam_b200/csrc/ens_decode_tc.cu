@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
   static_assert(P::off_W3e() == P::off_W0() + 32 * EMBP && TC_D3 == TC_D + 32, "[W0; W3e] and [D | D3] must be contiguous");
   extern __shared__ __align__(128) float smem[];
   float *sw = smem;                                     // the tc blob
+  float *stile = smem + P::total() + (threadIdx.x >> 5) * 1024;   // this warp's [32][32] gather staging tile
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127, gwarp = (tid >> 5) & 3;
@@ -219,14 +220,23 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
     }
 
     // ---- features -> TMEM (A operand of the folded feature GEMMs; read back for the output layer) ----
-    {
+    // Warp-cooperative gather (8 lanes per 128-byte voxel line, as in the mma kernels: a thread-per-point gather costs
+    // 8x the L1 wavefronts and was the kernel's top stall) into the warp's swizzled [32][32] staging tile; each thread
+    // then reads back its own row.
+#pragma unroll
+    for (int half = 0; half < CD / 32; ++half) {      // fine decoder: [fine | middle] concat (decoder.py:182-187)
+      const int lv = (half == 0) ? LEVEL : ENS_LEVEL_MIDDLE;
+      const Vox v = make_vox(pn, a.sc.dims[lv]);
+      __syncwarp();
+      gather_warp<32>(a.sc.grid[lv], a.sc.dims[lv], v, stile, 0);
       float f[32];
-      gather_regs(a.sc.grid[LEVEL], a.sc.dims[LEVEL], pn, f);
-      tmem_st32_split(tb + TC_FH, tb + TC_FL, f);
-      if (CD == 64) {      // fine decoder: [fine | middle] concat (decoder.py:182-187)
-        gather_regs(a.sc.grid[ENS_LEVEL_MIDDLE], a.sc.dims[ENS_LEVEL_MIDDLE], pn, f);
-        tmem_st32_split(tb + TC_FH + 32, tb + TC_FL + 32, f);
+      const int lane = tid & 31;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 x = *reinterpret_cast<const float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3)));
+        f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
       }
+      tmem_st32_split(tb + TC_FH + 32 * half, tb + TC_FL + 32 * half, f);
     }
     // ---- embedding chunks: D += e W0^T, D3 += e W3e^T ----
 #pragma unroll 1
@@ -324,7 +334,7 @@ template <int LEVEL, int CD, int NO>
 static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s) {
   TcArgs a;
   a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask;
-  const size_t smem = (size_t)MlpPackTC<CD>::total() * 4;
+  const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
