@@ -373,7 +373,7 @@ def run_gpu_arm(args):
     e2e = measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world)
 
     # ---- tracking iteration (config C2), reported beside the headline ----
-    track_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
+    track_ms, track_graph_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
     other = measure_other_configs(dev, renderer, decoders, c, frames, scene) if (rank == 0 and not args.no_other_configs) else None
     if other is not None and sharded is not None:
         other["full_frame_sharded"] = sharded
@@ -398,7 +398,7 @@ def run_gpu_arm(args):
             "config": workload_config(), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_timed, "gpu_launches_per_step": launches_timed / args.steps,
             "roofline": roof, "cpu_baseline": cpu,
-            "tracking_ms_per_iter": track_ms, "other_configs": other, "wall_s_timed_region": t_wall,
+            "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms, "other_configs": other, "wall_s_timed_region": t_wall,
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": eager_ms,
         }
@@ -527,19 +527,43 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
         loss = (torch.abs(sd - d) / torch.sqrt(u + 1e-10))[mask].sum() + 0.5 * torch.abs(sc_ - col)[mask].sum()
         loss.backward()
 
-    for _ in range(3):
-        it()
-    torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(iters):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); it(); b.record()
+    def it_capturable():
+        # the same iteration without host synchronisation: the boolean-mask selections become where() sums
+        ct.grad = None
+        c2w = common.get_camera_from_tensor(ct)
+        ro, rd, sd, sc_ = common.get_samples(100, cam.H - 100, 100, cam.W - 100, 200, cam.H, cam.W, cam.fx, cam.fy,
+                                             cam.cx, cam.cy, c2w, depth_t, color_t, dev)
+        d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, dev, "color", gt_depth=sd)
+        u = u.detach()
+        tmp = torch.abs(sd - d) / torch.sqrt(u + 1e-10)
+        mask = (tmp < 10 * tmp.median()) & (sd > 0)
+        loss = torch.where(mask, tmp, 0.0).sum() + 0.5 * torch.where(mask[:, None], torch.abs(sc_ - col), 0.0).sum()
+        loss.backward()
+        return loss
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
-        tot += a.elapsed_time(b)
+        tot = 0.0
+        for _ in range(iters):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / iters
+
+    eager_ms = timed(it)
+    graph_ms = None
+    try:
+        from evennicer_slam_b200.graph import GraphedStep
+        graph_ms = timed(GraphedStep(it_capturable, warmup=2, device=dev))
+    except Exception as e:      # pragma: no cover - reported, not fatal
+        sys.stderr.write(f"tracking graph capture failed: {e!r}\n")
     for p, r in zip(decoders.parameters(), req):
         p.requires_grad_(r)
-    return tot / iters
+    return eager_ms, graph_ms
 
 
 def measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world):
