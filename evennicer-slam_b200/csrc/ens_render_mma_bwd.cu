@@ -505,31 +505,49 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
         }
       }
       if (SPLIT) {
-        // dB[r][32jc + col] = sum_pt p[pt][r] g_q[pt][col]: per-lane partial over its four rows, butterfly over the
-        // eight row groups, RED from the four lanes of row group 0
+        // dB[r][32jc + col] = sum_pt p[pt][r] g_q[pt][col].  Per lane: partial over its four rows for its eight
+        // columns (slot cs = 2 nt + c2) x three components; then a reduce-SCATTER over the eight row groups (lane bits
+        // 2..4): each stage halves the slots a lane keeps, 12 + 6 + 3 shuffles instead of a 72-shuffle butterfly, and
+        // every lane ends with ONE column's three sums.
+        float sv[8][3];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int cs = 0; cs < 8; ++cs) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const int col = 32 * jc + 8 * nt + 2 * t + c2;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float q = acc[j >> 1][nt][2 * (j & 1) + c2];
-              s0 = fmaf(rx[j], q, s0); s1 = fmaf(ry[j], q, s1); s2 = fmaf(rz[j], q, s2);
-            }
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (g == 0 && col < EMB) {
-              atomicAdd(gdec + GO::off_B() + col, s0);
-              atomicAdd(gdec + GO::off_B() + EMB + col, s1);
-              atomicAdd(gdec + GO::off_B() + 2 * EMB + col, s2);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float q = acc[j >> 1][cs >> 1][2 * (j & 1) + (cs & 1)];
+            s0 = fmaf(rx[j], q, s0); s1 = fmaf(ry[j], q, s1); s2 = fmaf(rz[j], q, s2);
           }
+          sv[cs][0] = s0; sv[cs][1] = s1; sv[cs][2] = s2;
+        }
+        const bool b0 = g & 1, b1 = (g >> 1) & 1, b2 = (g >> 2) & 1;
+        float v4[4][3], v2[2][3], v1[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float mine = b0 ? sv[4 + k][r] : sv[k][r], send = b0 ? sv[k][r] : sv[4 + k][r];
+            v4[k][r] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float mine = b1 ? v4[2 + k][r] : v4[k][r], send = b1 ? v4[k][r] : v4[2 + k][r];
+            v2[k][r] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float mine = b2 ? v2[1][r] : v2[0][r], send = b2 ? v2[0][r] : v2[1][r];
+          v1[r] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+        const int cs = 4 * (int)b0 + 2 * (int)b1 + (int)b2;
+        const int col = 32 * jc + 8 * (cs >> 1) + 2 * t + (cs & 1);
+        if (col < EMB) {
+          atomicAdd(gdec + GO::off_B() + col, v1[0]);
+          atomicAdd(gdec + GO::off_B() + EMB + col, v1[1]);
+          atomicAdd(gdec + GO::off_B() + 2 * EMB + col, v1[2]);
+        }
       }
       if (WG) {
         store_tile<32>(w.sX, 0, ev, g, t);
