@@ -317,23 +317,36 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
 #pragma unroll
       for (int o = 0; o < NO; ++o) gr[j][o] = __shfl_sync(0xffffffffu, gout[o], g + 8 * j);
     if (WG || SPLIT) {
-      // dWo[o][n] = sum_pt gout[pt][o] h4[pt][n]; dbo[o] = sum_pt gout[pt][o]
+      // dWo[o][n] = sum_pt gout[pt][o] h4[pt][n]; dbo[o] = sum_pt gout[pt][o].  Per lane: partial over its four rows for
+      // its eight columns (slot cs = 2 nt + c); reduce-scatter over the eight row groups (4 + 2 + 1 shuffles per output).
+      const bool b0 = g & 1, b1 = (g >> 1) & 1, b2 = (g >> 2) & 1;
+      const int cs_mine = 4 * (int)b0 + 2 * (int)b1 + (int)b2;
+      const int col_mine = 8 * (cs_mine >> 1) + 2 * t + (cs_mine & 1);
 #pragma unroll
       for (int o = 0; o < NO; ++o) {
+        float sv[8];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            float s = gr[0][o] * acc[0][nt][c];
-            s = fmaf(gr[1][o], acc[0][nt][2 + c], s);
-            s = fmaf(gr[2][o], acc[1][nt][c], s);
-            s = fmaf(gr[3][o], acc[1][nt][2 + c], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            if (g == 0) atomicAdd(gdec + GO::off_Wo() + o * 32 + 8 * nt + 2 * t + c, s);
-          }
+        for (int cs = 0; cs < 8; ++cs) {
+          const int nt = cs >> 1, c = cs & 1;
+          float s = gr[0][o] * acc[0][nt][c];
+          s = fmaf(gr[1][o], acc[0][nt][2 + c], s);
+          s = fmaf(gr[2][o], acc[1][nt][c], s);
+          s = fmaf(gr[3][o], acc[1][nt][2 + c], s);
+          sv[cs] = s;
         }
+        float v4[4], v2[2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float mine = b0 ? sv[4 + k] : sv[k], send = b0 ? sv[k] : sv[4 + k];
+          v4[k] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float mine = b1 ? v4[2 + k] : v4[k], send = b1 ? v4[k] : v4[2 + k];
+          v2[k] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        const float mine = b2 ? v2[1] : v2[0], send = b2 ? v2[0] : v2[1];
+        atomicAdd(gdec + GO::off_Wo() + o * 32 + col_mine, mine + __shfl_xor_sync(0xffffffffu, send, 16));
         float sb = gout[o];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, off);
