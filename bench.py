@@ -587,14 +587,15 @@ def measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world):
         B = renderer.ray_batch_size
 
         def frame():
-            outs = []
-            for i in range(0, ro.shape[0], B):
-                outs.append(sharding.render_rays_sharded(renderer, c, decoders, rd[i:i + B], ro[i:i + B], dev, "color",
-                                                         gt_depth=depth_t[i:i + B]))
-            return outs
+            return sharding.render_frame_sharded(renderer, c, decoders, rd, ro, dev, "color", gt_depth=depth_t)
         outs = frame()
-        ref = renderer.render_batch_ray(c, decoders, rd[:B], ro[:B], dev, "color", gt_depth=depth_t[:B])
-        same = all(bool(torch.equal(a, b)) for a, b in zip(outs[0], ref))
+        # parity on real NCCL: two reference batches (the first and the ragged last) rendered unsharded
+        same = True
+        for i in (0, (ro.shape[0] // B) * B if ro.shape[0] % B else ro.shape[0] - B):
+            ref = renderer.render_batch_ray(c, decoders, rd[i:i + B], ro[i:i + B], dev, "color", gt_depth=depth_t[i:i + B])
+            same = same and all(bool(torch.equal(a[i:i + B], b)) for a, b in zip(outs, ref))
+        one = sharding.render_rays_sharded(renderer, c, decoders, rd[:B], ro[:B], dev, "color", gt_depth=depth_t[:B])
+        same = same and all(bool(torch.equal(a[:B], b)) for a, b in zip(outs, one))
         torch.cuda.synchronize(); dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

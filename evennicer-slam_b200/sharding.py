@@ -128,6 +128,69 @@ def render_rays_sharded(renderer, c, decoders, rays_d, rays_o, device, stage, gt
             allgather_rows(color, counts, group))
 
 
+_PERM_CACHE = {}
+
+
+def _frame_permutation(n: int, batch: int, w: int, device) -> torch.Tensor:
+    """Row index into the rank-major all-gathered block (every rank padded to the same length) for each ray of the
+    frame in frame order, when every reference batch of `batch` rays is split over the ranks with shard_range."""
+    key = (n, batch, w, str(device))
+    perm = _PERM_CACHE.get(key)
+    if perm is None:
+        per_rank = [0] * w
+        for i in range(0, n, batch):
+            m = min(batch, n - i)
+            for q in range(w):
+                lo, hi = shard_range(m, q, w)
+                per_rank[q] += hi - lo
+        pad = max(per_rank)
+        idx = torch.empty(n, dtype=torch.int64)
+        cursor = [0] * w
+        for i in range(0, n, batch):
+            m = min(batch, n - i)
+            for q in range(w):
+                lo, hi = shard_range(m, q, w)
+                idx[i + lo:i + hi] = torch.arange(q * pad + cursor[q], q * pad + cursor[q] + (hi - lo))
+                cursor[q] += hi - lo
+        perm = (idx.to(device), pad)
+        _PERM_CACHE[key] = perm
+    return perm
+
+
+def render_frame_sharded(renderer, c, decoders, rays_d, rays_o, device, stage, gt_depth=None, group=None):
+    """Renderer.render_img's batch loop over a whole frame on N ranks, no gradient: every reference batch
+    (renderer.ray_batch_size rays, whose two depth maxima each rank takes from its own copy of the depth image, so no
+    collective is needed for them) is split over the ranks; the ranks render their shards back to back and the frame
+    is assembled with ONE all-gather per output at the end.  Bit-identical to the unsharded loop."""
+    from .functional import depth_batch_max, render_batch_ray as _rbr
+    r, w = world(group)
+    n, B = rays_o.shape[0], renderer.ray_batch_size
+    setup = renderer._setup(stage, decoders, rays_o.device)
+    has_depth = gt_depth is not None and stage != "coarse"
+    gd_all = gt_depth.reshape(-1).float() if has_depth else None
+    outs = []
+    with torch.no_grad():
+        for i in range(0, n, B):
+            m = min(B, n - i)
+            lo, hi = shard_range(m, r, w)
+            dmax = depth_batch_max(gd_all[i:i + m].contiguous()) if has_depth else None
+            if hi > lo:
+                outs.append(_rbr(setup, c, decoders, rays_d[i + lo:i + hi], rays_o[i + lo:i + hi],
+                                 gd_all[i + lo:i + hi] if has_depth else None, depth_max=dmax))
+        if w == 1:
+            return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
+        perm, pad = _frame_permutation(n, B, w, rays_o.device)
+        res = []
+        for k, (dt, tail) in enumerate(((torch.float64, ()), (torch.float64, ()), (torch.float32, (3,)))):
+            local = torch.cat([o[k] for o in outs]) if outs else torch.empty((0,) + tail, dtype=dt, device=rays_o.device)
+            buf = torch.zeros((pad,) + tail, dtype=dt, device=rays_o.device)
+            buf[:local.shape[0]] = local
+            full = torch.empty((w * pad,) + tail, dtype=dt, device=rays_o.device)
+            dist.all_gather_into_tensor(full, buf, group=group)
+            res.append(full.index_select(0, perm))
+        return tuple(res)
+
+
 def eval_points_sharded(renderer, p, decoders, c, stage, device, group=None):
     """Renderer.eval_points over a point lattice split across ranks (mesh extraction, config 5)."""
     r, w = world(group)

@@ -37,6 +37,18 @@ def _worker(rank, world, port, q):
         sh.allreduce_sum_([v1, v2, v3], big_bytes=1 << 20)
         assert torch.all(v1 == tot) and torch.all(v2 == 2 * tot) and torch.all(v3 == 3 * tot)
         assert torch.all(arena[:4] == 0) and torch.all(arena[30:] == 0)
+        # frame permutation: rank-major padded blocks -> frame order, ragged last batch
+        perm, pad = sh._frame_permutation(23, 10, world, "cpu")
+        blocks = []
+        for rk in range(world):
+            rows = []
+            for i in range(0, 23, 10):
+                m = min(10, 23 - i)
+                a0, a1 = sh.shard_range(m, rk, world)
+                rows.extend(range(i + a0, i + a1))
+            blocks.append(rows + [-1] * (pad - len(rows)))
+        flat = torch.tensor([x for b in blocks for x in b])
+        assert torch.equal(flat[perm], torch.arange(23))
         # ragged all-gather
         rows = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
         counts = [sh.shard_range(11, r, world)[1] - sh.shard_range(11, r, world)[0] for r in range(world)]
