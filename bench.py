@@ -255,6 +255,9 @@ def run_gpu_arm(args):
     from evennicer_slam_b200 import common, harness, sharding, functional, _lib
     from evennicer_slam_b200.functional import TIMER
 
+    if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+        # the camera tensors are created on the default stream and used on the per-keyframe streams (intended)
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     scene, frames = make_inputs()
     decoders, c, renderer, cfg = harness.build(scene, dev, native_layout=not args.reference_grid_layout)
     cam = scene.cam
@@ -316,7 +319,7 @@ def run_gpu_arm(args):
     if use_graph:
         from evennicer_slam_b200.graph import GraphedStep
         zero_grads()                      # grads are then (re)allocated from the graph's private pool
-        run_step = GraphedStep(step, warmup=2, device=dev)
+        run_step = GraphedStep(step, warmup=2, device=dev, before_capture=zero_grads)
         for _ in range(3):
             run_step()
         torch.cuda.synchronize()
@@ -677,6 +680,153 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
                            "frac_of_hbm_roofline": n / ms * 1e3 * 2048 / (hbm_peak()[0] * 1e9)}
     for p, r in zip(decoders.parameters(), req):
         p.requires_grad_(r)
+    out.update(measure_mapping_variants(dev, renderer, decoders, c, frames, scene))
+    return out
+
+
+def _mapping_batch(dev, scene, frames, n_rays, seed):
+    """`n_rays` mapping rays drawn from the keyframes with the reference's pixel draw (common.get_samples), fixed."""
+    import torch
+    from evennicer_slam_b200 import common
+    cam = scene.cam
+    torch.manual_seed(seed)
+    per = n_rays // len(frames)
+    ros, rds, sds, scs = [], [], [], []
+    for (cam_t, depth, color) in frames:
+        c2w = common.get_camera_from_tensor(torch.from_numpy(cam_t.copy()).to(dev))
+        ro, rd, sd, sc_ = common.get_samples(0, cam.H, 0, cam.W, per, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy, c2w,
+                                             torch.from_numpy(depth).to(dev), torch.from_numpy(color).to(dev), dev)
+        ros.append(ro.float()); rds.append(rd.float()); sds.append(sd.float()); scs.append(sc_.float())
+    return [torch.cat(x).detach() for x in (ros, rds, sds, scs)]
+
+
+def measure_mapping_variants(dev, renderer, decoders, c, frames, scene):
+    """SURVEY.md 8(d) C3 beside the headline: the mapping step per stage and as the reference's 60-iteration schedule
+    (Mapper.py:462-467: 25 middle, 12 fine, 23 colour), a large batch (65 536 rays: the throughput regime, where the
+    1000-ray step is latency-bound), and the same 1000-ray step on the RPG recording4 scene (197 MiB of grids > L2).
+    Rays are fixed; each entry is render_batch_ray + Mapper loss + backward into grids, decoders and rays."""
+    import torch
+    import evennicer_slam_b200.synthetic as syn
+    from evennicer_slam_b200 import harness
+    from evennicer_slam_b200.graph import GraphedStep
+    peak = hbm_peak()[0] * 1e9
+    out = {}
+    grids = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    params = list(decoders.parameters())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def make_step(rend, dec, g, batch, stage):
+        ro, rd, sd, sc_ = batch
+        ro = ro.clone().requires_grad_(True); rd = rd.clone().requires_grad_(True)
+
+        def step():
+            rend._cache.invalidate()
+            depth, unc, color = rend.render_batch_ray(g, dec, rd, ro, dev, stage, gt_depth=sd)
+            loss = torch.where(sd > 0, torch.abs(sd - depth), 0.0).sum()
+            if stage == "color":
+                loss = loss + 0.2 * torch.abs(sc_ - color).sum()
+            loss.backward()
+        return step, [ro, rd]
+
+    def clear(ts):
+        for t in ts:
+            t.grad = None
+
+    def timed(fn, reps):
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    # -- per stage, graph-replayed, 1000 rays -------------------------------------------------------------------
+    batch = _mapping_batch(dev, scene, frames, N_RAYS, 31)
+    lf = {"middle": 1, "fine": 2, "color": 3}
+    replay = {}
+    for stage in ("middle", "fine", "color"):
+        step, leaves = make_step(renderer, decoders, grids, batch, stage)
+        every = leaves + list(grids.values()) + params
+        for _ in range(3):
+            clear(every); step()
+        torch.cuda.synchronize(); clear(every)
+        replay[stage] = GraphedStep(step, warmup=2, device=dev, before_capture=lambda: clear(every))
+        replay[stage](); replay[stage](); torch.cuda.synchronize()
+        ms = timed(replay[stage], 15)
+        bytes_per_ray = 3 * 1024 * lf[stage] * S_TOTAL
+        out[f"mapping_stage_{stage}"] = {"rays": N_RAYS, "ms": ms, "rays_per_s": N_RAYS / ms * 1e3,
+                                         "frac_of_hbm_roofline": N_RAYS / ms * 1e3 * bytes_per_ray / peak}
+    sched = [("middle", 25), ("fine", 12), ("color", 23)]
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for stage, k in sched:
+        for _ in range(k):
+            replay[stage]()
+    b.record(); torch.cuda.synchronize()
+    out["mapping_schedule_60_iters"] = {"iters": {s_: k for s_, k in sched}, "ms_total": a.elapsed_time(b),
+                                        "note": "render + loss + backward only (no optimizer step), no L2 flush between iterations"}
+    del replay
+
+    # -- large batch, eager (launch overhead is negligible at this size) ------------------------------------------
+    n_big = 65536 // N_FRAMES * N_FRAMES
+    big = _mapping_batch(dev, scene, frames, n_big, 32)
+    step, leaves = make_step(renderer, decoders, grids, big, "color")
+    every = leaves + list(grids.values()) + params
+
+    def big_step():
+        clear(every); step()
+    big_step(); big_step(); torch.cuda.synchronize()
+    ms = timed(big_step, 5)
+    out["mapping_large_batch"] = {"rays": n_big, "ms": ms, "rays_per_s": n_big / ms * 1e3,
+                                  "frac_of_hbm_roofline": n_big / ms * 1e3 * BYTES_PER_RAY / peak}
+    del big, step, leaves, every
+    clear(list(grids.values()) + params)
+    torch.cuda.empty_cache()
+
+    # -- the mapper's event branch (Mapper.py:591): 102 x 180 rescaled frame rendered WITH gradients into grids,
+    #    decoders and the camera tensor (the tracker's variant, pose only, is `event_render` above)
+    from evennicer_slam_b200 import common
+    cam_t, depth, _ = frames[-1]
+    depth_t = torch.from_numpy(depth).to(dev)
+    ct = torch.from_numpy(cam_t.copy()).to(dev).requires_grad_(True)
+    every = [ct] + list(grids.values()) + params
+
+    def event_map():
+        clear(every)
+        renderer._cache.invalidate()
+        c2w = common.get_camera_from_tensor(ct)
+        d, u, col = renderer.render_img_rescale(grids, decoders, c2w, dev, "color", gt_depth=depth_t, scale_factor=0.15)
+        col.sum().backward()
+    event_map(); event_map(); torch.cuda.synchronize()
+    ms = timed(event_map, 5)
+    n_ev = int(scene.cam.H * 0.15) * int(scene.cam.W * 0.15)
+    out["mapping_event_render"] = {"rays": n_ev, "ms": ms, "rays_per_s": n_ev / ms * 1e3,
+                                   "frac_of_hbm_roofline": n_ev / ms * 1e3 * BYTES_PER_RAY / peak}
+    clear(every)
+
+    # -- RPG recording4 scene: grids larger than L2 ---------------------------------------------------------------
+    rscene = syn.make_scene(syn.RPG4_BOUND, syn.RPG_CAM, seed=20, name="rpg4", grid_std={"fine": 0.01})
+    rdec, rc, rrend, _ = harness.build(rscene, dev, native_layout=True)
+    rframes = []
+    for f in range(N_FRAMES):
+        cam_t = syn.default_pose(syn.RPG4_BOUND, jitter_seed=10 + f)
+        depth, color, _ = syn.synthetic_frame(syn.RPG4_BOUND, syn.RPG_CAM, cam_t, seed=100 + f, zero_frac=0.02)
+        rframes.append((cam_t, depth, color))
+    rgrids = {k: v.clone().requires_grad_(True) for k, v in rc.items()}
+    rbatch = _mapping_batch(dev, rscene, rframes, N_RAYS, 33)
+    step, leaves = make_step(rrend, rdec, rgrids, rbatch, "color")
+    every = leaves + list(rgrids.values()) + list(rdec.parameters())
+    for _ in range(3):
+        clear(every); step()
+    torch.cuda.synchronize(); clear(every)
+    g = GraphedStep(step, warmup=2, device=dev, before_capture=lambda: clear(every))
+    g(); g(); torch.cuda.synchronize()
+    ms = timed(g, 15)
+    out["mapping_rpg_recording4"] = {"rays": N_RAYS, "grid_mib": sum(v.numel() * 4 for v in rc.values()) / 2 ** 20, "ms": ms,
+                                     "rays_per_s": N_RAYS / ms * 1e3,
+                                     "frac_of_hbm_roofline": N_RAYS / ms * 1e3 * BYTES_PER_RAY / peak}
     return out
 
 

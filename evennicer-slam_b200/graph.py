@@ -11,7 +11,9 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn, warmup: int = 3, device=None):
+    def __init__(self, fn, warmup: int = 3, device=None, before_capture=None):
+        """`before_capture` runs after the warm-up calls and before the capture -- e.g. setting ``.grad = None`` on the
+        leaves, so the captured backward hands its gradient buffers over instead of adding into the warm-up's."""
         self.fn = fn
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         cur = torch.cuda.current_stream(dev)
@@ -22,6 +24,8 @@ class GraphedStep:
                 fn()
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        if before_capture is not None:
+            before_capture()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = fn()
