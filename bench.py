@@ -681,6 +681,96 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
     for p, r in zip(decoders.parameters(), req):
         p.requires_grad_(r)
     out.update(measure_mapping_variants(dev, renderer, decoders, c, frames, scene))
+    out.update(measure_grid_adam(dev))
+    return out
+
+
+def measure_grid_adam(dev):
+    """the fused frustum-masked Adam step (ens_grid_adam_step) on the middle/fine/colour grids,
+    the voxels inside one camera frustum selected, against the reference's own sequence on the same GPU (boolean-mask index_put into the
+    grid, torch.optim.Adam.step on the gathered copies, boolean-mask write-back: Mapper.py:451-458, 625, 633-641).
+    HBM-bound: a selected voxel moves 7 lines of 128 B (value, gradient, two moments in; value, two moments out)
+    plus its 4-byte index."""
+    import torch
+    import evennicer_slam_b200.synthetic as syn
+    from evennicer_slam_b200 import scene as scn
+    from evennicer_slam_b200.optim import FrustumGridAdam
+    import cases
+    peak = hbm_peak()[0] * 1e9
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    keys = ("grid_middle", "grid_fine", "grid_color")
+    lrs = {k: 0.005 for k in keys}
+
+    def timed(fn, reps=10):
+        fn(); fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            # cold AND clean L2: the write flush alone would leave ~120 MB of dirty lines whose write-back lands in the
+            # timed kernel's HBM traffic; a read pass over the same buffer replaces them with clean ones
+            flush.fill_(1); flush.view(torch.int64).sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    def frustum_mask(sc, shape):
+        """voxel centres inside the view frustum of the scene's default pose (the shape of Mapper.get_mask_from_c2w's
+        selection, without its depth test): spatially coherent, unlike a random mask"""
+        b = sc.bound
+        Z, Y, X = shape
+        zs, ys, xs = torch.meshgrid(torch.linspace(float(b[2, 0]), float(b[2, 1]), Z, device=dev),
+                                    torch.linspace(float(b[1, 0]), float(b[1, 1]), Y, device=dev),
+                                    torch.linspace(float(b[0, 0]), float(b[0, 1]), X, device=dev), indexing="ij")
+        pts = torch.stack([xs, ys, zs], -1).reshape(-1, 3)
+        c2w = torch.from_numpy(syn.quat_to_c2w(syn.default_pose(np.asarray(b).tolist(), jitter_seed=10))).float().to(dev)
+        pc = (pts - c2w[:3, 3]) @ c2w[:3, :3]                   # camera coordinates (x right, y up, z backward)
+        cam = sc.cam
+        z = -pc[:, 2]
+        u = cam.fx * pc[:, 0] / z.clamp_min(1e-5) + cam.cx
+        v = -cam.fy * pc[:, 1] / z.clamp_min(1e-5) + cam.cy
+        m = (z > 0) & (u > 0) & (u < cam.W) & (v > 0) & (v < cam.H)
+        m |= ((pts - c2w[:3, 3]) ** 2).sum(-1) < 0.25
+        return m.reshape(Z, Y, X)
+
+    for name, sc in (("room0", cases.room0_scene()),
+                     ("rpg_recording4", syn.make_scene(syn.RPG4_BOUND, syn.RPG_CAM, seed=20, name="rpg4"))):
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        c = {k: scn.as_native_layout(torch.from_numpy(sc.grids[k]).to(dev)).requires_grad_(True) for k in keys}
+        masks = {k: frustum_mask(sc, tuple(c[k].shape[2:])) for k in keys}
+        for k in keys:
+            c[k].grad = scn.as_native_layout(torch.randn(c[k].shape, device=dev, generator=gen) * 1e-3)
+        opt = FrustumGridAdam(c, masks)
+        ms = timed(lambda: opt.step(lrs))
+        n_sel = sum(int(masks[k].sum()) for k in keys)
+        n_vox = sum(masks[k].numel() for k in keys)
+        bytes_ = n_sel * (7 * 128 + 4)
+        opt_all = FrustumGridAdam(c, None)                          # every voxel: the selection-independent upper case
+        ms_all = timed(lambda: opt_all.step(lrs))
+        out[f"grid_adam_{name}_all_voxels"] = {"voxels": n_vox, "selected": n_vox, "ms": ms_all,
+                                               "gbs": n_vox * 7 * 128 / ms_all / 1e6,
+                                               "frac_of_hbm_peak": n_vox * 7 * 128 / (ms_all * 1e-3) / peak}
+        del opt_all
+        # the reference sequence, eager torch on the same GPU
+        cr = {k: c[k].detach().clone().contiguous() for k in keys}
+        full = {k: masks[k][None, None].repeat(1, 32, 1, 1, 1) for k in keys}
+        vg = {k: cr[k][full[k]].clone().requires_grad_(True) for k in keys}
+        topt = torch.optim.Adam([{"params": [vg[k]], "lr": lrs[k]} for k in keys])
+        dense = {k: c[k].grad.contiguous() for k in keys}
+
+        def ref_seq():
+            for k in keys:
+                val = cr[k]; val[full[k]] = vg[k].detach()          # Mapper.py:455-457
+                vg[k].grad = dense[k][full[k]]                      # what index_put's backward hands the copy
+            topt.step()                                             # :625
+            for k in keys:
+                cr[k][full[k]] = vg[k].detach().clone()             # :637-640
+        ms_ref = timed(ref_seq, 5)
+        out[f"grid_adam_{name}"] = {"voxels": n_vox, "selected": n_sel, "ms": ms, "gbs": bytes_ / ms / 1e6,
+                                    "frac_of_hbm_peak": bytes_ / (ms * 1e-3) / peak,
+                                    "torch_reference_sequence_ms": ms_ref}
+        del c, cr, full, vg, topt, dense, opt, masks
+        torch.cuda.empty_cache()
     return out
 
 

@@ -19,7 +19,7 @@ STAGE_LEVELS = {"coarse": ("coarse",), "middle": ("middle",), "fine": ("middle",
                 "color": ("middle", "fine", "color")}
 
 ENS_OK = 0
-ABI_VERSION = 3            # include/ens_render.h: ENS_ABI_VERSION
+ABI_VERSION = 4            # include/ens_render.h: ENS_ABI_VERSION
 
 
 class EnsScene(C.Structure):
@@ -34,6 +34,11 @@ class EnsRenderCfg(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_surface", C.c_int32), ("n_importance", C.c_int32),
                 ("lindisp", C.c_int32), ("perturb", C.c_float), ("occupancy", C.c_int32),
                 ("t_vals", C.c_void_p), ("t_vals_surface", C.c_void_p)]
+
+
+class EnsAdamLevel(C.Structure):
+    _fields_ = [("grid", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("voxel_index", C.c_void_p), ("n_selected", C.c_int64), ("n_voxels", C.c_int64), ("lr", C.c_double)]
 
 
 class EnsGrads(C.Structure):
@@ -74,6 +79,8 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.POINTER(EnsGrads), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_int, C.c_void_p]),
+    "ens_grid_adam_step": (C.c_int, [C.POINTER(EnsAdamLevel), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,107 @@
+"""Frustum-masked Adam on the feature grids, fused into one launch.
+
+The reference's mapper optimises a gathered COPY of the grid features inside the current view frustum
+(``frustum_feature_selection``, Mapper.py:343-361), scatters the copy into the grid before every render (:451-458),
+steps ``torch.optim.Adam`` on it (:396-423, :625) and scatters it back (:633-641) -- three boolean-mask passes over up to
+5.7 M elements per level and iteration, each with an implicit ``nonzero`` host sync.  ``FrustumGridAdam`` keeps the grids
+whole, in the render kernels' layout, and applies the same update in place to the selected voxels with one kernel that
+reads the dense gradient the render backward produced (``ens_grid_adam_step``).
+
+    opt = FrustumGridAdam(c, masks)            # once per optimize_map call, like the reference's optimizer (:396)
+    for joint_iter in range(n):
+        ...render, loss.backward()...          # c[key].grad is dense, as in the reference without feature selection
+        opt.step({'grid_middle': lr_m, 'grid_fine': lr_f, 'grid_color': lr_c})
+        opt.zero_grad()
+
+Semantics are those of the reference sequence: selected voxels (all 32 channels) take the Adam update with zero-initialised
+moments and a step count starting at 1; every other voxel keeps its value.  Learning rate 0 (a stage that freezes a level,
+configs/nice_slam.yaml:45-76) still advances the moments, exactly as torch.optim.Adam does with lr = 0.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .scene import is_native_strided
+
+
+def _native_base(t: torch.Tensor) -> torch.Tensor:
+    """The contiguous [Z,Y,X,32] tensor a native-strided [1,32,Z,Y,X] view aliases."""
+    return t.detach()[0].permute(1, 2, 3, 0)
+
+
+class FrustumGridAdam:
+    def __init__(self, c: Dict[str, torch.Tensor], masks: Optional[Dict[str, Optional[torch.Tensor]]] = None,
+                 betas=(0.9, 0.999), eps: float = 1e-8, graph_safe: bool = False):
+        """c: the scene dict; every grid to optimise must be in the native layout (``scene.as_native_layout``).
+        masks: per key a bool/uint8 voxel mask [Z,Y,X] (``torch.from_numpy(mask).permute(2,1,0)`` of
+        ``Mapper.get_mask_from_c2w``) or None = every voxel.  graph_safe: keep step and learning rates in device memory
+        so a captured CUDA graph can replay ``step`` (advance them with ``set_dynamic`` outside the graph)."""
+        self.keys = [k for k in c if masks is None or k in masks]
+        if not 0 < len(self.keys) <= 4:
+            raise ValueError("FrustumGridAdam optimises 1..4 grids")
+        self.c = c
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        self.state = {}
+        self.masks = {}
+        for k in self.keys:
+            g = c[k]
+            if not (g.is_cuda and g.dtype == torch.float32 and is_native_strided(g)):
+                raise ValueError(f"{k}: FrustumGridAdam needs a float32 CUDA grid in the native layout "
+                                 "(scene.as_native_layout)")
+            base = _native_base(g)
+            self.state[k] = (torch.zeros_like(base), torch.zeros_like(base))
+            m = None if masks is None else masks.get(k)
+            if m is not None:
+                if tuple(m.shape) != tuple(g.shape[2:]):
+                    raise ValueError(f"{k}: voxel mask must be [Z,Y,X] = {tuple(g.shape[2:])}, got {tuple(m.shape)}")
+                # the selection as an ascending voxel list, once per optimiser (= per optimize_map call); the
+                # reference re-derives it inside every boolean-mask index_put (nonzero + host sync each time)
+                m = torch.nonzero(m.to(device=g.device).reshape(-1) != 0).reshape(-1).to(torch.int32).contiguous()
+            self.masks[k] = m
+        dev = c[self.keys[0]].device
+        self.dyn = torch.zeros(1 + len(self.keys), dtype=torch.float64, device=dev) if graph_safe else None
+
+    def set_dynamic(self, step: int, lrs: Dict[str, float]) -> None:
+        """graph_safe mode: write the step number and learning rates the next replayed ``step`` will use."""
+        vals = [float(step)] + [float(lrs.get(k, 0.0)) for k in self.keys]
+        self.dyn.copy_(torch.tensor(vals, dtype=torch.float64), non_blocking=True)
+
+    def step(self, lrs: Dict[str, float], clear_grad: bool = False) -> None:
+        L = _lib.lib()
+        n = len(self.keys)
+        arr = (_lib.EnsAdamLevel * n)()
+        keep = []
+        for i, k in enumerate(self.keys):
+            g = self.c[k]
+            grad = g.grad
+            if grad is None:
+                raise RuntimeError(f"{k}.grad is None: run the render backward before FrustumGridAdam.step")
+            if not is_native_strided(grad):       # a gradient that did not come from the fused backward
+                grad = grad.contiguous()[0].permute(1, 2, 3, 0).contiguous().permute(3, 0, 1, 2).unsqueeze(0)
+                if clear_grad:
+                    raise RuntimeError("clear_grad needs the native-layout gradient of the fused backward")
+            gb, base = _native_base(grad), _native_base(g)
+            m, v = self.state[k]
+            keep.append(gb)
+            arr[i].grid, arr[i].grad = base.data_ptr(), gb.data_ptr()
+            arr[i].exp_avg, arr[i].exp_avg_sq = m.data_ptr(), v.data_ptr()
+            arr[i].n_voxels = base.shape[0] * base.shape[1] * base.shape[2]
+            arr[i].voxel_index = None if self.masks[k] is None else self.masks[k].data_ptr()
+            arr[i].n_selected = arr[i].n_voxels if self.masks[k] is None else self.masks[k].numel()
+            arr[i].lr = float(lrs.get(k, 0.0))
+        self.step_count += 1
+        from .functional import TIMER
+        TIMER.launches += 1
+        dev = self.c[self.keys[0]].device
+        _lib.check(L.ens_grid_adam_step(arr, n, self.betas[0], self.betas[1], self.eps, self.step_count,
+                                        _lib.ptr(self.dyn), 1 if clear_grad else 0, _lib.cur_stream(dev)),
+                   "ens_grid_adam_step")
+
+    def zero_grad(self) -> None:
+        for k in self.keys:
+            self.c[k].grad = None

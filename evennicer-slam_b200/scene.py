@@ -47,7 +47,9 @@ def is_native_strided(grid: torch.Tensor) -> bool:
     if grid.dim() != 5 or grid.shape[0] != 1:
         return False
     _, Cc, Z, Y, X = grid.shape
-    return tuple(grid.stride()[1:]) == (1, Y * X * Cc, X * Cc, Cc)
+    want = (1, Y * X * Cc, X * Cc, Cc)
+    # the stride of a size-1 dimension is arbitrary (torch keeps whatever the producing op left there)
+    return all(n == 1 or st == w for n, st, w in zip(grid.shape[1:], grid.stride()[1:], want))
 
 
 def as_native_layout(grid: torch.Tensor) -> torch.Tensor:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ENS_ABI_VERSION 3
+#define ENS_ABI_VERSION 4
 
 typedef void *ens_stream_t; /* cudaStream_t */
 
@@ -180,6 +180,32 @@ int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, co
                    const float *raw, const double *g_depth, const double *g_var, const float *g_color,
                    const EnsGrads *grads, void *workspace, int64_t workspace_bytes, const void *saved,
                    int64_t saved_bytes, int saved_with_activations, ens_stream_t stream);
+
+/* ---- fused frustum-masked Adam step on the feature grids ---------------------------------
+ * One launch replaces, for every grid level of a mapping iteration (src/Mapper.py): the boolean-mask gather of the
+ * optimisable features (:343-361), the index_put of them into the grid before each render (:451-458),
+ * torch.optim.Adam.step on the grid parameter groups (:396-423, :625; default betas/eps, no weight decay, no amsgrad)
+ * and the write-back (:633-641).  All buffers are in the NATIVE layout [Z][Y][X][32]; `grad` is the dense gradient
+ * ens_render_bwd accumulated.  The voxels listed in voxel_index (the nonzero positions of the frustum mask
+ * `torch.from_numpy(mask).permute(2,1,0)` flattened over [Z][Y][X], ascending, built once per optimize_map call) are
+ * updated, all 32 channels (Mapper.py:345-346); other voxels and their moments are left untouched.  voxel_index == NULL
+ * selects every voxel (n_selected must equal n_voxels).  exp_avg / exp_avg_sq are dense, caller-owned, zero-initialised
+ * when the optimiser is created (one per optimize_map call in the reference).
+ * step: 1-based Adam step of this call.  dyn: NULL, or a DEVICE double[1 + n_levels] = {step, lr[0..n_levels)} read by the
+ * kernel instead of `step` / `lr` -- lets a captured CUDA graph advance the step and change the stage's learning rates.
+ * clear_grad: also zero `grad` of the voxels it updates. */
+typedef struct EnsAdamLevel {
+  float *grid;               /* native layout, updated in place                          */
+  float *grad;               /* native layout; const unless clear_grad                   */
+  float *exp_avg;            /* first moment, native layout                              */
+  float *exp_avg_sq;         /* second moment, native layout                             */
+  const int32_t *voxel_index;/* device int32 [n_selected], ascending, or NULL = every voxel */
+  int64_t n_selected;        /* number of selected voxels                                */
+  int64_t n_voxels;          /* Z*Y*X (< 2^31)                                           */
+  double lr;                 /* cfg['mapping']['stage'][stage]['<level>_lr'] * lr_factor */
+} EnsAdamLevel;
+int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double beta1, double beta2, double eps,
+                       int64_t step, const double *dyn, int clear_grad, ens_stream_t stream);
 
 #ifdef __cplusplus
 }
