@@ -682,7 +682,46 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
         p.requires_grad_(r)
     out.update(measure_mapping_variants(dev, renderer, decoders, c, frames, scene))
     out.update(measure_grid_adam(dev))
+    out.update(measure_event_loss(dev))
     return out
+
+
+def measure_event_loss(dev):
+    """blurred-L2 event loss, value + gradient (Tracker.py:204-224; kernel 9, weight 1, balancer
+    0.025: configs/Replica/replica.yaml:8-13) on the 102 x 180 x 2 event image -- the fused launch against the reference's
+    torchvision lines run eagerly on the same GPU."""
+    import torch
+    from torchvision import transforms
+    from evennicer_slam_b200.losses import event_loss
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    gt = torch.poisson(torch.full((102, 180, 2), 0.3, device=dev), generator=gen)
+    pred = (torch.rand((102, 180, 2), device=dev, generator=gen) * 1.5).requires_grad_(True)
+
+    def fused():
+        pred.grad = None
+        loss, _ = event_loss(gt, pred, [9], [1.0], 0.025)
+        loss.backward()
+
+    def ref():
+        pred.grad = None
+        loss = ((gt - pred) ** 2).sum()
+        g = transforms.functional.gaussian_blur(gt.permute(2, 0, 1), kernel_size=9).permute(1, 2, 0)
+        p = transforms.functional.gaussian_blur(pred.permute(2, 0, 1), kernel_size=9).permute(1, 2, 0)
+        loss = (loss + 1.0 * ((g - p) ** 2).sum()) * 0.025
+        loss.backward()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+    return {"event_loss_102x180": {"ms": timed(fused), "torchvision_reference_lines_ms": timed(ref),
+                                   "note": "eager, loss + backward to the predicted event image"}}
 
 
 def measure_grid_adam(dev):

@@ -207,6 +207,21 @@ typedef struct EnsAdamLevel {
 int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double beta1, double beta2, double eps,
                        int64_t step, const double *dyn, int clear_grad, ens_stream_t stream);
 
+/* ---- blurred-L2 event loss, value + gradient in one launch ------------------------------
+ * Replaces src/Tracker.py:204-224 and src/Mapper.py:593-615:
+ *     loss = ((gt - pred)**2).sum() + sum_k w_k * ((gaussian_blur(gt, ks_k) - gaussian_blur(pred, ks_k))**2).sum()
+ *     loss *= balancer;  loss.backward()
+ * gaussian_blur = torchvision.transforms.functional.gaussian_blur on a tensor: reflect padding by ks/2 and a depthwise
+ * conv2d with the outer product of the normalised 1-d kernel (sigma = 0.15 ks + 0.35 by default).
+ * gt, pred: device float32 [H][W][C] (the layout of gt_event / full_event in the reference).
+ * kernel_sizes_host[n_kernels] (odd, <= 15), kernels1d_host: the 1-d kernels back to back (sum ks_k floats, as
+ * torchvision's _get_gaussian_kernel1d computes them in float32), kernel_weights_host[n_kernels]; n_kernels <= 4.
+ * loss_parts: device double[2 + n_kernels] = {balancer * total, sum (gt-pred)^2, blurred sum per kernel} (overwritten).
+ * g_pred: device float32 [H][W][C] = d(loss_parts[0]) / d pred (overwritten), or NULL. */
+int ens_event_loss(const float *gt, const float *pred, int H, int W, int C, const int *kernel_sizes_host,
+                   const float *kernels1d_host, const float *kernel_weights_host, int n_kernels, float balancer,
+                   double *loss_parts, float *g_pred, ens_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
