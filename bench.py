@@ -376,7 +376,7 @@ def run_gpu_arm(args):
     e2e = measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world)
 
     # ---- tracking iteration (config C2), reported beside the headline ----
-    track_ms, track_graph_ms = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
+    track_ms, track_graph_ms, track_fused = measure_tracking(dev, renderer, decoders, c, frames, scene, flush)
     other = measure_other_configs(dev, renderer, decoders, c, frames, scene) if (rank == 0 and not args.no_other_configs) else None
     if other is not None and sharded is not None:
         other["full_frame_sharded"] = sharded
@@ -401,7 +401,8 @@ def run_gpu_arm(args):
             "config": workload_config(), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_timed, "gpu_launches_per_step": launches_timed / args.steps,
             "roofline": roof, "cpu_baseline": cpu,
-            "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms, "other_configs": other, "wall_s_timed_region": t_wall,
+            "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms,
+            "tracking_ms_per_iter_fused_loss": track_fused, "other_configs": other, "wall_s_timed_region": t_wall,
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": eager_ms,
         }
@@ -557,16 +558,31 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
             tot += a.elapsed_time(b)
         return tot / iters
 
+    def it_fused():
+        # Tracker.py:180-196 through losses.tracker_loss (one launch for the loss and its gradients)
+        from evennicer_slam_b200.losses import tracker_loss
+        ct.grad = None
+        c2w = common.get_camera_from_tensor(ct)
+        ro, rd, sd, sc_ = common.get_samples(100, cam.H - 100, 100, cam.W - 100, 200, cam.H, cam.W, cam.fx, cam.fy,
+                                             cam.cx, cam.cy, c2w, depth_t, color_t, dev)
+        d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, dev, "color", gt_depth=sd)
+        loss = tracker_loss(sd, sc_, d, u, col, 0.5, True, True)
+        loss.backward()
+        return loss
+
     eager_ms = timed(it)
     graph_ms = None
+    fused = {}
     try:
         from evennicer_slam_b200.graph import GraphedStep
         graph_ms = timed(GraphedStep(it_capturable, warmup=2, device=dev))
+        fused["eager_ms"] = timed(it_fused)
+        fused["graph_ms"] = timed(GraphedStep(it_fused, warmup=2, device=dev))
     except Exception as e:      # pragma: no cover - reported, not fatal
         sys.stderr.write(f"tracking graph capture failed: {e!r}\n")
     for p, r in zip(decoders.parameters(), req):
         p.requires_grad_(r)
-    return eager_ms, graph_ms
+    return eager_ms, graph_ms, fused
 
 
 def measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world):
@@ -886,6 +902,24 @@ def measure_mapping_variants(dev, renderer, decoders, c, frames, scene):
         bytes_per_ray = 3 * 1024 * lf[stage] * S_TOTAL
         out[f"mapping_stage_{stage}"] = {"rays": N_RAYS, "ms": ms, "rays_per_s": N_RAYS / ms * 1e3,
                                          "frac_of_hbm_roofline": N_RAYS / ms * 1e3 * bytes_per_ray / peak}
+    # the colour-stage step with the mapper's loss as ONE launch (losses.mapper_loss)
+    from evennicer_slam_b200.losses import mapper_loss
+    ro_f = batch[0].clone().requires_grad_(True); rd_f = batch[1].clone().requires_grad_(True)
+
+    def step_fused():
+        renderer._cache.invalidate()
+        depth, unc, color = renderer.render_batch_ray(grids, decoders, rd_f, ro_f, dev, "color", gt_depth=batch[2])
+        mapper_loss(batch[2], batch[3], depth, color, 0.2, True).backward()
+    every = [ro_f, rd_f] + list(grids.values()) + params
+    for _ in range(3):
+        clear(every); step_fused()
+    torch.cuda.synchronize(); clear(every)
+    gf = GraphedStep(step_fused, warmup=2, device=dev, before_capture=lambda: clear(every))
+    gf(); gf(); torch.cuda.synchronize()
+    ms = timed(gf, 15)
+    out["mapping_stage_color_fused_loss"] = {"rays": N_RAYS, "ms": ms, "rays_per_s": N_RAYS / ms * 1e3,
+                                             "frac_of_hbm_roofline": N_RAYS / ms * 1e3 * BYTES_PER_RAY / peak}
+    del gf
     sched = [("middle", 25), ("fine", 12), ("color", 23)]
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

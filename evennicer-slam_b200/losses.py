@@ -1,5 +1,11 @@
-"""Fused loss glue around the renderer: the blurred-L2 event loss of Tracker.py:204-224 and
-Mapper.py:593-615 as ONE launch that returns the loss and its gradient with respect to the predicted event image.
+"""Fused loss glue around the renderer.
+
+* ``mapper_loss`` / ``tracker_loss``: the RGB-D losses of Mapper.py:553-562 and
+  Tracker.py:180-196 -- value and the gradients with respect to the rendered depth and colour in ONE launch instead of
+  ~25 eager ones (abs, sqrt, median, boolean-mask gathers with their host syncs, sums, and their autograd transposes).
+  No boolean indexing means no host sync: the whole iteration can be captured in a CUDA graph.
+* ``event_loss``: the blurred-L2 event loss of Tracker.py:204-224 and Mapper.py:593-615 as ONE
+  launch that returns the loss and its gradient with respect to the predicted event image.
 
     loss, parts = event_loss(gt_event, full_event, kernel_sizes=[9], kernel_weights=[1], balancer=0.025)
     loss.backward()                       # gradient flows into full_event (the UNet output) as in the reference
@@ -74,3 +80,62 @@ def event_loss(gt_event: torch.Tensor, full_event: torch.Tensor, kernel_sizes: S
     if not blur:
         kernel_sizes, kernel_weights = (), ()
     return _EventLoss.apply(full_event, gt_event, tuple(kernel_sizes), tuple(kernel_weights), float(balancer))
+
+
+class _RgbdLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, color, uncertainty, gt_depth, gt_color, tracker, use_color, w_color, handle_dynamic):
+        if not depth.is_cuda:
+            raise RuntimeError("the fused RGB-D losses need CUDA tensors (there is no CPU fallback)")
+        L = _lib.lib()
+        n = depth.shape[0]
+        d = depth.detach().to(torch.float64).contiguous()
+        gd = gt_depth.detach().to(torch.float32).contiguous()
+        col = gcol = None
+        f64 = 0
+        if use_color:
+            col = color.detach().to(torch.float32).contiguous()
+            gcol = gt_color.detach().contiguous()
+            if gcol.dtype == torch.float64:
+                f64 = 1
+            elif gcol.dtype != torch.float32:
+                gcol = gcol.float()
+            if tuple(col.shape) != (n, 3) or tuple(gcol.shape) != (n, 3):
+                raise ValueError("color and gt_color must be [n,3]")
+        var = uncertainty.detach().to(torch.float64).contiguous() if tracker else None
+        work = torch.empty(n, dtype=torch.float64, device=d.device) if tracker else None
+        loss = torch.empty(1, dtype=torch.float64, device=d.device)
+        need_d, need_c = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and use_color
+        g_d = torch.empty_like(d) if need_d else None
+        g_c = torch.empty_like(col) if need_c else None
+        from .functional import TIMER
+        TIMER.launches += 1
+        _lib.check(L.ens_rgbd_loss(1 if tracker else 0, _lib.ptr(d), _lib.ptr(var), _lib.ptr(col), _lib.ptr(gd),
+                                   _lib.ptr(gcol), f64, n, 1 if use_color else 0, float(w_color),
+                                   1 if handle_dynamic else 0, _lib.ptr(loss), _lib.ptr(g_d), _lib.ptr(g_c),
+                                   _lib.ptr(work), _lib.cur_stream(d.device)), "ens_rgbd_loss")
+        ctx.g = (g_d, g_c)
+        ctx.dtypes = (depth.dtype, color.dtype if color is not None else None)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        g_d, g_c = ctx.g
+        gd = (g_d * g_loss).to(ctx.dtypes[0]) if g_d is not None else None
+        gc = (g_c * g_loss.to(torch.float32)).to(ctx.dtypes[1]) if g_c is not None else None
+        return gd, gc, None, None, None, None, None, None, None
+
+
+def mapper_loss(batch_gt_depth, batch_gt_color, depth, color, w_color_loss: float = 0.2, use_color: bool = True):
+    """Mapper.py:553-562: ``|gt_depth - depth|[gt_depth > 0].sum() (+ w * |gt_color - color|.sum())`` -> float64 scalar.
+    ``use_color`` is the reference's ``(not self.nice) or (self.stage == 'color')``."""
+    return _RgbdLoss.apply(depth, color if use_color else None, None, batch_gt_depth,
+                           batch_gt_color if use_color else None, False, use_color, w_color_loss, False)
+
+
+def tracker_loss(batch_gt_depth, batch_gt_color, depth, uncertainty, color, w_color_loss: float = 0.2,
+                 use_color_in_tracking: bool = True, handle_dynamic: bool = True):
+    """Tracker.py:180-196 (uncertainty is detached there, and here): -> float64 scalar."""
+    return _RgbdLoss.apply(depth, color if use_color_in_tracking else None, uncertainty, batch_gt_depth,
+                           batch_gt_color if use_color_in_tracking else None, True, use_color_in_tracking,
+                           w_color_loss, handle_dynamic)

@@ -222,6 +222,21 @@ int ens_event_loss(const float *gt, const float *pred, int H, int W, int C, cons
                    const float *kernels1d_host, const float *kernel_weights_host, int n_kernels, float balancer,
                    double *loss_parts, float *g_pred, ens_stream_t stream);
 
+/* ---- RGB-D loss glue of the callers, value + gradients in one launch ----------------------
+ * tracker = 0 (src/Mapper.py:553-562):  loss = sum_{gt_depth>0} |gt_depth - depth|  (+ w_color * sum |gt_color - color|
+ *                                       when use_color: the mapper's colour stage; the colour term is NOT masked)
+ * tracker = 1 (src/Tracker.py:180-196): tmp = |gt_depth - depth| / sqrt(uncertainty + 1e-10)   (uncertainty detached)
+ *                                       mask = (gt_depth > 0) [& tmp < 10 * median(tmp) when handle_dynamic]
+ *                                       loss = sum_mask tmp (+ w_color * sum_mask |gt_color - color| when use_color)
+ * median = torch.median: the lower middle element, found exactly.  All arithmetic float64, as in the reference.
+ * depth, uncertainty: device double[n]; color: float[n][3]; gt_depth: float[n]; gt_color: float or double [n][3].
+ * loss: device double[1] (overwritten); g_depth: double[n] = d loss / d depth, g_color: float[n][3] = d loss / d color
+ * (overwritten; either may be NULL); workspace: device double[n], tracker only. */
+int ens_rgbd_loss(int tracker, const double *depth, const double *uncertainty, const float *color, const float *gt_depth,
+                  const void *gt_color, int gt_color_is_f64, int64_t n, int use_color, double w_color,
+                  int handle_dynamic, double *loss, double *g_depth, float *g_color, double *workspace,
+                  ens_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
