@@ -147,6 +147,8 @@ struct TcArgs {
   int64_t n;
   float *out4;            // [n][4]
   int apply_mask;         // last launch of the stage and the caller wants the bound rule
+  uint32_t *msave;        // optional: this decoder's saved relu masks, one word per point and block --
+                          // [n_tiles32][5][32], word (tile, i, j) = point 32 tile + j, bit k = unit k of block i active
 };
 
 // Two 128-point tiles are in flight per CTA: tile group 0 = warps 0-3, group 1 = warps 4-7; each owns 256 TMEM columns,
@@ -273,6 +275,12 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
       const float *bi = sw + P::off_b(0) + 32 * i;
 #pragma unroll
       for (int k = 0; k < 32; ++k) r[k] = fmaxf(r[k] + bi[k], 0.f);
+      if (a.msave != nullptr && valid) {          // saved for a pose-only backward (render_bwd_mma_kernel, mask_fmt 1)
+        uint32_t mw = 0u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mw |= (r[k] > 0.f ? 1u : 0u) << k;
+        a.msave[(pt >> 5) * 160 + i * 32 + (pt & 31)] = mw;
+      }
       if (i < 4) {
         tmem_st32_split(tb + TC_XH, tb + TC_XL, r);
         tmem_st_done();
@@ -331,9 +339,10 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
 }
 
 template <int LEVEL, int CD, int NO>
-static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s) {
+static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s,
+                            uint32_t *msave = nullptr) {
   TcArgs a;
-  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave;
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -352,14 +361,16 @@ static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_
 }
 
 // NICE.forward / Renderer.eval_points for stages middle, fine, color: one launch per decoder of the stage.
+// msave / mstride: optional saved-mask buffer of the stage (decoder d = middle, fine, colour at msave + d * mstride words).
 int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
-                   float *out4, cudaStream_t s) {
+                   float *out4, cudaStream_t s, uint32_t *msave, int64_t mstride) {
   if (stage == ENS_STAGE_COARSE) return ENS_EUNSUPPORTED;
-  int rc = launch_decode_tc<ENS_LEVEL_MIDDLE, 32, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_MIDDLE ? apply_mask : 0, out4, s);
+  int rc = launch_decode_tc<ENS_LEVEL_MIDDLE, 32, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_MIDDLE ? apply_mask : 0, out4, s, msave);
   if (rc != ENS_OK || stage == ENS_STAGE_MIDDLE) return rc;
-  rc = launch_decode_tc<ENS_LEVEL_FINE, 64, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_FINE ? apply_mask : 0, out4, s);
+  rc = launch_decode_tc<ENS_LEVEL_FINE, 64, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_FINE ? apply_mask : 0, out4, s,
+                                               msave ? msave + mstride : nullptr);
   if (rc != ENS_OK || stage == ENS_STAGE_FINE) return rc;
-  return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s);
+  return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s, msave ? msave + 2 * mstride : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -440,7 +451,7 @@ int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, c
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   place_kernel<<<g, NT_MMA, 0, s>>>(a.sc, a.ra, z, pts);
   ENS_CHECK_CUDA();
-  const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s);
+  const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s, a.save_masks, a.n_tiles * 160);
   if (rc != ENS_OK) return rc;
   composite_kernel<<<(unsigned)((a.ra.R + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4 *>(raw), z, a.ra.R, a.ra.S,
                                                                     a.depth, a.var, a.color, a.w_out);

@@ -214,6 +214,7 @@ struct BwdArgs {
   const uint32_t *save_masks;   // from the forward (null: recompute)
   const float *save_h;          // from the forward (null: recompute when decoder grads are wanted)
   int64_t n_tiles;
+  int mask_fmt;                 // 0: words in the mma kernels' lane layout; 1: one word per point (tcgen05 forward)
   const float *raw;
   const double *g_depth, *g_var;
   const float *g_color;
@@ -270,7 +271,7 @@ int mma_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f
 int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s);
 // tcgen05 variant (ens_decode_tc.cu)
 int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
-                   float *out4, cudaStream_t s);
+                   float *out4, cudaStream_t s, uint32_t *msave = nullptr, int64_t mstride = 0);
 int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s);
 int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage);
 int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset);

@@ -946,17 +946,26 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   fill_ray_args(a.ra, cfg, stage, rays_o, rays_d, gt_depth, depth_max, n_rays, S, ns);
   a.depth = depth; a.var = var; a.color = color; a.z_out = z_vals; a.w_out = weights; a.raw_out = raw;
   a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0;
+  if (saved_with_activations < 0 || saved_with_activations > 2) return ENS_EINVAL;
+  const bool want_h = saved_with_activations == 1;
   if (saved != nullptr) {
     int64_t n_tiles = 0, h_off = 0;
-    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, saved_with_activations, &n_tiles, &h_off);
+    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, want_h, &n_tiles, &h_off);
     if (need > 0) {
       if (saved_bytes < need || (reinterpret_cast<uintptr_t>(saved) & 15)) return ENS_ESHAPE;
       a.save_masks = reinterpret_cast<uint32_t *>(saved);
-      a.save_h = saved_with_activations ? reinterpret_cast<float *>(reinterpret_cast<char *>(saved) + h_off) : nullptr;
+      a.save_h = want_h ? reinterpret_cast<float *>(reinterpret_cast<char *>(saved) + h_off) : nullptr;
       a.n_tiles = n_tiles;
     }
   }
   cudaStream_t s = (cudaStream_t)stream;
+  if (saved_with_activations == 2) {
+    // masks as one word per point, written by the tcgen05 decode: the forward of a pose-only backward (tracking, event
+    // render).  The caller tells ens_render_bwd the same kind, so there is no silent change of format: anything that
+    // prevents this path is an error.
+    if (a.save_masks == nullptr || !use_mma_forward() || !use_mma_backward()) return ENS_EUNSUPPORTED;
+    return tc_render_fwd(a, stage, scratch, scratch_bytes, s);
+  }
   if (use_mma_forward() && a.save_masks == nullptr && scratch != nullptr) {
     // no backward will follow and the caller gave scratch: placement + tcgen05 decode + compositing
     const char *v = std::getenv("ENS_EVAL_VARIANT");
@@ -1029,15 +1038,21 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   wg = n_dec > 0;
   a.g_rays_o = grads->rays_o; a.g_rays_d = grads->rays_d;
   a.hscratch = (float *)workspace;
-  a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0;
+  a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0; a.mask_fmt = 0;
+  if (saved_with_activations < 0 || saved_with_activations > 2) return ENS_EINVAL;
+  const bool have_h = saved_with_activations == 1;
+  if (saved_with_activations == 2 && (saved == nullptr || !use_mma_backward())) return ENS_EUNSUPPORTED;
   if (saved != nullptr && use_mma_backward()) {
     int64_t n_tiles = 0, h_off = 0;
-    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, saved_with_activations, &n_tiles, &h_off);
+    const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, have_h, &n_tiles, &h_off);
     if (need > 0) {
       if (saved_bytes < need) return ENS_ESHAPE;
       a.save_masks = reinterpret_cast<const uint32_t *>(saved);
-      a.save_h = saved_with_activations ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(saved) + h_off) : nullptr;
+      a.save_h = have_h ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(saved) + h_off) : nullptr;
       a.n_tiles = n_tiles;
+      a.mask_fmt = saved_with_activations == 2 ? 1 : 0;
+    } else if (saved_with_activations == 2) {
+      return ENS_EUNSUPPORTED;
     }
   }
   const bool saved_covers = a.save_masks != nullptr && (!wg || a.save_h != nullptr);

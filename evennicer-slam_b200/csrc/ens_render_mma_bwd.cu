@@ -305,9 +305,27 @@ __device__ __forceinline__ void decoder_bwd_mma(const BwdArgs &a, float *__restr
       if (WG && i < 4) store_tile<32>(w.hs + i * 1024, 0, acc, g, t);      // h_i = x_{i+1}
     }
     } else {
-      const uint32_t *ms = a.save_masks + (((int64_t)DEC * a.n_tiles + w.gtile) * 5) * 32 + lane;
+      const uint32_t *mt = a.save_masks + (((int64_t)DEC * a.n_tiles + w.gtile) * 5) * 32;
+      if (a.mask_fmt == 0) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) mask[k] = ms[k * 32];
+        for (int k = 0; k < 5; ++k) mask[k] = mt[k * 32 + lane];
+      } else {
+        // one word per point (bit n = unit n), written by the tcgen05 forward: gather the words of my four rows and
+        // re-order their bits into the accumulator-fragment order  bit ((m*4 + nt)*4 + e) <- row 16m + g + 8(e>>1),
+        // unit 8nt + 2t + (e&1)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          uint32_t mk = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                          // row g + 8j: m = j >> 1, e>>1 = j & 1
+            const uint32_t pw = mt[k * 32 + g + 8 * j];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+              mk |= ((pw >> (8 * nt + 2 * t)) & 3u) << ((((j >> 1) * 4 + nt) * 4) + 2 * (j & 1));
+          }
+          mask[k] = mk;
+        }
+      }
       if (WG || SPLIT) load_tile<32>(hsrc + 4 * 1024, 0, acc, g, t);        // h_4 for dWo
     }
     // decoder-output gradients of my four rows

@@ -6,6 +6,7 @@ All arithmetic is in ``csrc/*.cu``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -17,6 +18,7 @@ from .scene import SceneCache, build_scene_struct, decoder_grad_views, is_native
 
 TC_MIN_POINTS = 1         # every forward-only call takes the placement + tcgen05 decode + compositing path (one variant for all
                           # batch sizes keeps the forward bit-independent of how a frame is cut into batches)
+TC_POSE_FORWARD = os.environ.get("ENS_FWD_TC_MASKS", "1") != "0"   # tcgen05 forward when only masks are kept
 SAVE_FORWARD = True    # keep relu masks / activations from the forward kernel for the backward (False: it recomputes)
 _DEBUG: Dict[str, object] = {}     # test hook: set _DEBUG["keep_workspace"]=True to inspect the backward scratch
 
@@ -144,25 +146,31 @@ class _RenderBatchRay(torch.autograd.Function):
         want_bwd = any(needs[6:])
         want_dec = want_bwd and any(needs[8 + n_grids:])
         saved = None
+        saved_kind = 1 if want_dec else 0          # 0: relu masks, 1: masks + activations, 2: masks from the tcgen05 forward
         if want_bwd and SAVE_FORWARD:
             nbytes = int(L.ens_fwd_saved_bytes(R, S, STAGES[setup.stage], int(want_dec)))
             if nbytes > 0:
                 saved = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
         scratch = None
-        if saved is None and not want_bwd and R * S >= TC_MIN_POINTS:
-            # forward only (render_img, visualisation) and a large batch: scratch for the three-kernel tcgen05 path
+        tc_forward = (not want_bwd) or (saved is not None and not want_dec and TC_POSE_FORWARD)
+        if tc_forward and R * S >= TC_MIN_POINTS:
+            # no activations to keep (forward only: render_img, visualisation; or a backward without decoder gradients:
+            # tracking, the tracker's event render): scratch for the placement -> tcgen05 decode -> compositing path
             nbytes = int(L.ens_fwd_scratch_bytes(R, S, STAGES[setup.stage]))
             if nbytes > 0:
                 scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+                if saved is not None:
+                    saved_kind = 2
         stream = _lib.cur_stream(dev)
         _lib.check(TIMER.launch("render_fwd", dev, lambda: L.ens_render_fwd(
             C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd),
             _lib.ptr(depth_max) if has_depth else None, R, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color),
             _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0,
-            int(want_dec), _lib.ptr(scratch), scratch.numel() * 8 if scratch is not None else 0,
+            saved_kind, _lib.ptr(scratch), scratch.numel() * 8 if scratch is not None else 0,
             stream)), "ens_render_fwd")
         ctx.saved_fwd = saved
         ctx.saved_has_h = bool(want_dec)
+        ctx.saved_kind = saved_kind
         ctx.grid_native_strided = [is_native_strided(g) for g in grids]
         ctx.setup = setup
         ctx.levels = levels
@@ -245,7 +253,7 @@ class _RenderBatchRay(torch.autograd.Function):
             C.byref(sc), C.byref(cfg), STAGES[setup.stage], _lib.ptr(ro), _lib.ptr(rd),
             _lib.ptr(gd) if ctx.has_depth else None, _lib.ptr(depth_max) if ctx.has_depth else None, R,
             _lib.ptr(raw), _lib.ptr(gdp), _lib.ptr(gvp), _lib.ptr(gcp), C.byref(grads), _lib.ptr(ws), ws_bytes,
-            _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0, int(ctx.saved_has_h),
+            _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0, ctx.saved_kind if saved is not None else 0,
             stream)), "ens_render_bwd")
         if _DEBUG.get("keep_workspace"):
             _DEBUG["workspace"] = ws

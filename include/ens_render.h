@@ -161,9 +161,12 @@ int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_i
  * device double[2] from ens_depth_max (NULL iff gt_depth is NULL).
  * Outputs: depth f64 [R], var f64 [R], color f32 [R][3].  Optional (may be NULL): z_vals f64 [R][S],
  * weights f32 [R][S], raw f32 [R][S][4] (pre-sigmoid; `raw` is also what ens_render_bwd wants back).
- * saved / saved_bytes: optional buffer of ens_fwd_saved_bytes(n_rays, S, stage, saved_with_activations) bytes,
+ * saved / saved_bytes: optional buffer of ens_fwd_saved_bytes(n_rays, S, stage, saved_with_activations == 1) bytes,
  * filled for ens_render_bwd (16-byte aligned; NULL = the backward recomputes).
- * scratch / scratch_bytes: optional, see ens_fwd_scratch_bytes (only used when saved is NULL). */
+ * saved_with_activations: 0 = relu masks only (enough for a backward without decoder gradients), 1 = masks + hidden
+ * activations (decoder gradients), 2 = masks only, written by the tcgen05 decode path (placement -> decode -> compositing;
+ * needs `scratch`; ENS_EUNSUPPORTED if that path cannot run) -- pass the same value to ens_render_bwd.
+ * scratch / scratch_bytes: optional, see ens_fwd_scratch_bytes (used when saved is NULL or saved_with_activations == 2). */
 int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                    const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
                    double *depth, double *var, float *color, double *z_vals, float *weights, float *raw,

@@ -622,3 +622,37 @@ def test_graphed_mapping_step_equals_eager(tiny):
     assert len(got) == len(ref)
     for a, b in zip(got, ref):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+
+
+def test_tcgen05_forward_feeds_the_pose_only_backward(tiny):
+    """A backward without decoder gradients (tracking, the tracker's event render) keeps only relu masks; they then come
+    from the tcgen05 decode path as one word per point (saved kind 2).  Same outputs and ray gradients as the mma.sync
+    forward with lane-layout masks, for every stage that has the path, and the oracle's gradients."""
+    from evennicer_slam_b200 import functional
+    renderer, decoders, c, g = tiny["renderer"], tiny["decoders"], tiny["c"], tiny["g"]
+    req = [p.requires_grad for p in decoders.parameters()]
+    for p in decoders.parameters():
+        p.requires_grad_(False)
+    try:
+        for stage in ("middle", "fine", "color"):
+            tag = f"{stage}.d"
+            sd = torch.from_numpy(g[f"{tag}.sample_depth"]).to(DEV)
+            n = sd.shape[0]
+            g_d, g_v, g_c = cases.upstream_grads(n)
+            res = {}
+            for use_tc in (True, False):
+                functional.TC_POSE_FORWARD = use_tc
+                ro = torch.from_numpy(g[f"{tag}.rays_o"]).to(DEV).requires_grad_(True)
+                rd = torch.from_numpy(g[f"{tag}.rays_d"]).to(DEV).requires_grad_(True)
+                d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, DEV, stage, gt_depth=sd)
+                ((d * torch.from_numpy(g_d).to(DEV)).sum() + (u * torch.from_numpy(g_v).to(DEV)).sum()
+                 + (col.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+                res[use_tc] = [x.detach().cpu().numpy() for x in (d, u, col, ro.grad, rd.grad)]
+            for a, b in zip(res[True], res[False]):
+                assert rel_err(a, b) < TOL_OUT
+            assert rel_err(res[True][0], g[f"{tag}.depth"]) < TOL_OUT
+            assert rel_err(res[True][3], g[f"{tag}.g_rays_o"]) < TOL_GRAD and rel_err(res[True][4], g[f"{tag}.g_rays_d"]) < TOL_GRAD
+    finally:
+        functional.TC_POSE_FORWARD = True
+        for p, r in zip(decoders.parameters(), req):
+            p.requires_grad_(r)
