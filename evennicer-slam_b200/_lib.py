@@ -81,6 +81,10 @@ _SIGNATURES = {
                                  C.c_int, C.c_void_p]),
     "ens_grid_adam_step": (C.c_int, [C.POINTER(EnsAdamLevel), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int64,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "ens_tensors_adam_step": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p,
+                                        C.c_void_p]),
     "ens_event_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),

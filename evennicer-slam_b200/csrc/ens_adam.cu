@@ -126,9 +126,97 @@ __global__ void __launch_bounds__(ADAM_THREADS) grid_adam_kernel(const AdamArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adam over many small tensors in one launch: the decoder weights (69 tensors, 58 956 floats) and the camera tensors of
+// the reference's optimizer (Mapper.py:396-423: groups with their own learning rate).  torch.optim.Adam walks them with
+// a dozen multi-tensor launches per step (more in its capturable form); here blockIdx.y is the tensor.
+// ---------------------------------------------------------------------------------------------
+constexpr int MT_MAX = 96;
+
+struct MultiAdamArgs {
+  float *param[MT_MAX];
+  const float *grad[MT_MAX];
+  int size[MT_MAX];
+  int state_off[MT_MAX];
+  unsigned char group[MT_MAX];
+  float step_size[8];            // lr / bias_correction1 per group (dyn == nullptr)
+  float *m, *v;                  // flat moments, tensor i at state_off[i]
+  float beta1, beta2, one_m_beta1, one_m_beta2, eps, inv_bc2_sqrt;
+  double beta1_d, beta2_d;
+  const double *dyn;             // device [1 + n_groups]: step, lr per group
+  int n_groups;
+};
+
+__global__ void __launch_bounds__(256) multi_adam_kernel(const __grid_constant__ MultiAdamArgs a) {
+  const int ti = blockIdx.y;
+  const int n = a.size[ti];
+  const int i0 = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= n) return;
+  float step_size, ibc2s;
+  if (a.dyn) {
+    const double step = a.dyn[0];
+    step_size = (float)(a.dyn[1 + a.group[ti]] / (1.0 - pow(a.beta1_d, step)));
+    ibc2s = (float)(1.0 / sqrt(1.0 - pow(a.beta2_d, step)));
+  } else {
+    step_size = a.step_size[a.group[ti]];
+    ibc2s = a.inv_bc2_sqrt;
+  }
+  float *p = a.param[ti];
+  const float *g = a.grad[ti];
+  float *m = a.m + a.state_off[ti], *v = a.v + a.state_off[ti];
+  for (int i = i0; i < n; i += gridDim.x * 256) {
+    const float gk = g[i];
+    const float mk = fmaf(gk, a.one_m_beta1, m[i] * a.beta1);
+    const float vk = fmaf(gk * gk, a.one_m_beta2, v[i] * a.beta2);
+    const float denom = sqrtf(vk) * ibc2s + a.eps;
+    p[i] = p[i] - step_size * (mk / denom);
+    m[i] = mk;
+    v[i] = vk;
+  }
+}
+
 }  // namespace ens
 
 using namespace ens;
+
+extern "C" int ens_tensors_adam_step(float *const *params_host, const float *const *grads_host, const int64_t *sizes_host,
+                                     const int *groups_host, int n_tensors, const double *lrs_host, int n_groups,
+                                     float *exp_avg, float *exp_avg_sq, double beta1, double beta2, double eps,
+                                     int64_t step, const double *dyn, ens_stream_t stream) {
+  if (n_tensors < 0 || n_groups < 1 || n_groups > 8 || (step < 1 && !dyn)) return ENS_EINVAL;
+  if (n_tensors == 0) return ENS_OK;
+  if (!params_host || !grads_host || !sizes_host || !groups_host || !lrs_host || !exp_avg || !exp_avg_sq) return ENS_EINVAL;
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) return ENS_EINVAL;
+  const double bc1 = dyn ? 1.0 : 1.0 - pow(beta1, (double)step);
+  int64_t off_total = 0;
+  for (int base = 0; base < n_tensors; base += MT_MAX) {        // more tensors than one launch holds: several launches
+    MultiAdamArgs a{};
+    const int cnt = n_tensors - base < MT_MAX ? n_tensors - base : MT_MAX;
+    int max_n = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int j = base + i;
+      if (!params_host[j] || !grads_host[j] || sizes_host[j] < 0 || sizes_host[j] > 0x7fffffffLL) return ENS_EINVAL;
+      if (groups_host[j] < 0 || groups_host[j] >= n_groups) return ENS_EINVAL;
+      a.param[i] = params_host[j]; a.grad[i] = grads_host[j]; a.size[i] = (int)sizes_host[j];
+      a.state_off[i] = (int)off_total; a.group[i] = (unsigned char)groups_host[j];
+      off_total += sizes_host[j];
+      if (off_total > 0x7fffffffLL) return ENS_ESHAPE;
+      if (a.size[i] > max_n) max_n = a.size[i];
+    }
+    for (int gq = 0; gq < n_groups; ++gq) a.step_size[gq] = (float)(lrs_host[gq] / bc1);
+    a.m = exp_avg; a.v = exp_avg_sq;
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+    a.one_m_beta1 = (float)(1.0 - beta1); a.one_m_beta2 = (float)(1.0 - beta2);
+    a.eps = (float)eps; a.beta1_d = beta1; a.beta2_d = beta2; a.dyn = dyn; a.n_groups = n_groups;
+    if (!dyn) a.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
+    if (max_n == 0) continue;
+    int gx = (max_n + 255) / 256;
+    if (gx > 64) gx = 64;
+    multi_adam_kernel<<<dim3(gx, cnt), 256, 0, (cudaStream_t)stream>>>(a);
+    ENS_CHECK_CUDA();
+  }
+  return ENS_OK;
+}
 
 extern "C" int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double beta1, double beta2, double eps,
                                   int64_t step, const double *dyn, int clear_grad, ens_stream_t stream) {

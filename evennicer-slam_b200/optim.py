@@ -105,3 +105,82 @@ class FrustumGridAdam:
     def zero_grad(self) -> None:
         for k in self.keys:
             self.c[k].grad = None
+
+
+class FusedAdam:
+    """``torch.optim.Adam`` for the small parameter groups of the reference's optimizers (decoder weights, camera tensors;
+    Mapper.py:396-423, Tracker.py:326-333) as ONE launch per step (``ens_tensors_adam_step``).
+
+    Mirrors the part of the torch API the reference uses: ``FusedAdam([{'params': [...], 'lr': 0}, ...])``,
+    ``opt.param_groups[i]['lr'] = ...``, ``opt.step()``, ``opt.zero_grad()``; default betas / eps, no weight decay, no
+    amsgrad.  Parameters whose ``.grad`` is None at a step are skipped, as torch does.  ``graph_safe``: step number and
+    learning rates live in device memory (``set_dynamic``) so a captured CUDA graph can replay ``step``.
+    """
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, graph_safe: bool = False):
+        groups = list(params)
+        if groups and not isinstance(groups[0], dict):
+            groups = [{"params": groups}]
+        self.param_groups = [{"params": list(g["params"]), "lr": float(g.get("lr", lr))} for g in groups]
+        if not 1 <= len(self.param_groups) <= 8:
+            raise ValueError("FusedAdam takes 1..8 parameter groups")
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        flat = [p for g in self.param_groups for p in g["params"]]
+        if not flat:
+            raise ValueError("FusedAdam got an empty parameter list")
+        for p in flat:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise ValueError("FusedAdam needs contiguous float32 CUDA parameters (there is no CPU fallback)")
+        dev = flat[0].device
+        total = sum(p.numel() for p in flat)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.dyn = torch.zeros(1 + len(self.param_groups), dtype=torch.float64, device=dev) if graph_safe else None
+        self._dev = dev
+
+    def set_dynamic(self, step: int, lrs=None) -> None:
+        lrs = [g["lr"] for g in self.param_groups] if lrs is None else list(lrs)
+        self.dyn.copy_(torch.tensor([float(step)] + [float(x) for x in lrs], dtype=torch.float64), non_blocking=True)
+
+    def step(self) -> None:
+        L = _lib.lib()
+        ps, gs, sizes, grp, offs = [], [], [], [], []
+        off = 0
+        keep = []
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                n = p.numel()
+                if p.grad is not None:
+                    gr = p.grad if (p.grad.is_contiguous() and p.grad.dtype == torch.float32) else p.grad.float().contiguous()
+                    keep.append(gr)
+                    ps.append(p.data_ptr()); gs.append(gr.data_ptr()); sizes.append(n); grp.append(gi); offs.append(off)
+                off += n
+        self.step_count += 1
+        if not ps:
+            return
+        from .functional import TIMER
+        # the moments of a skipped tensor must not shift the others: one call per run of consecutive state offsets
+        i = 0
+        lrs = (C.c_double * len(self.param_groups))(*[g["lr"] for g in self.param_groups])
+        while i < len(ps):
+            j = i + 1
+            while j < len(ps) and offs[j] == offs[j - 1] + sizes[j - 1]:
+                j += 1
+            n = j - i
+            TIMER.launches += 1
+            _lib.check(L.ens_tensors_adam_step(
+                (C.c_void_p * n)(*ps[i:j]), (C.c_void_p * n)(*gs[i:j]), (C.c_int64 * n)(*sizes[i:j]),
+                (C.c_int * n)(*grp[i:j]), n, lrs, len(self.param_groups),
+                C.c_void_p(self.exp_avg.data_ptr() + 4 * offs[i]), C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * offs[i]),
+                self.betas[0], self.betas[1], self.eps, self.step_count, _lib.ptr(self.dyn),
+                _lib.cur_stream(self._dev)), "ens_tensors_adam_step")
+            i = j
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for g in self.param_groups:
+            for p in g["params"]:
+                if set_to_none:
+                    p.grad = None
+                elif p.grad is not None:
+                    p.grad.zero_()

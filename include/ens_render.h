@@ -210,6 +210,17 @@ typedef struct EnsAdamLevel {
 int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double beta1, double beta2, double eps,
                        int64_t step, const double *dyn, int clear_grad, ens_stream_t stream);
 
+/* Adam over many small tensors in ONE launch: the other parameter groups of the mapper's optimizer (decoder weights,
+ * camera tensors; src/Mapper.py:396-423, :625) and the tracker's camera tensor (src/Tracker.py:326-333).  Same
+ * arithmetic as ens_grid_adam_step.  params_host / grads_host / sizes_host / groups_host: host arrays of n_tensors device
+ * pointers, element counts and group indices; lrs_host[n_groups] (n_groups <= 8); exp_avg / exp_avg_sq: device float
+ * buffers of sum(sizes) elements, tensor i at the sum of the sizes before it, zero-initialised by the caller.
+ * dyn: NULL or device double[1 + n_groups] = {step, lr per group} read at run time (CUDA-graph replays). */
+int ens_tensors_adam_step(float *const *params_host, const float *const *grads_host, const int64_t *sizes_host,
+                          const int *groups_host, int n_tensors, const double *lrs_host, int n_groups, float *exp_avg,
+                          float *exp_avg_sq, double beta1, double beta2, double eps, int64_t step, const double *dyn,
+                          ens_stream_t stream);
+
 /* ---- blurred-L2 event loss, value + gradient in one launch ------------------------------
  * Replaces src/Tracker.py:204-224 and src/Mapper.py:593-615:
  *     loss = ((gt - pred)**2).sum() + sum_k w_k * ((gaussian_blur(gt, ks_k) - gaussian_blur(pred, ks_k))**2).sum()

@@ -142,3 +142,36 @@ def test_mapping_iterations_with_fused_adam_follow_the_reference_sequence():
         assert np.abs(a - s).max() > 1e-3
         # the first steps of Adam move every touched feature by ~lr whatever its gradient: compare to the step size
         assert np.abs(a - b).max() < 1e-3 * np.abs(a - s).max(), (k, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("graph_safe", [False, True])
+def test_fused_adam_matches_torch_adam_on_decoder_shaped_groups(graph_safe):
+    """FusedAdam (ens_tensors_adam_step) against torch.optim.Adam on the same CUDA tensors: decoder-shaped tensors in one
+    group, camera tensors in another (different learning rates, changed mid-way as the stages do), one parameter that
+    never receives a gradient (torch skips it; so must we, without shifting the other moments)."""
+    from evennicer_slam_b200.optim import FusedAdam
+    torch.manual_seed(5)
+    shapes = [(32, 32), (32,), (3, 93), (32, 93), (32, 125), (4, 32), (4,), (1,)]
+    pa = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    cams = [torch.randn(7, device=DEV).requires_grad_(True) for _ in range(4)]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    camsb = [p.detach().clone().requires_grad_(True) for p in cams]
+    ref = torch.optim.Adam([{"params": pa, "lr": 0.005}, {"params": cams, "lr": 0.001}])
+    opt = FusedAdam([{"params": pb, "lr": 0.005}, {"params": camsb, "lr": 0.001}], graph_safe=graph_safe)
+    skip = 2                                                       # pa[2] / pb[2] never get a gradient
+    for it in range(6):
+        if it == 3:
+            ref.param_groups[0]["lr"] = 0.0; opt.param_groups[0]["lr"] = 0.0      # a stage that freezes the decoders
+        for k, (a, b) in enumerate(zip(pa + cams, pb + camsb)):
+            if k == skip:
+                continue
+            gr = torch.randn_like(a) * 10 ** float(torch.empty(1).uniform_(-4, 0))
+            a.grad = gr.clone(); b.grad = gr.clone()
+        ref.step()
+        if graph_safe:
+            opt.set_dynamic(it + 1)
+        opt.step()
+    torch.cuda.synchronize()
+    for k, (a, b) in enumerate(zip(pa + cams, pb + camsb)):
+        a, b = a.detach().cpu().numpy(), b.detach().cpu().numpy()
+        assert np.all(np.abs(a - b) <= 2e-6 * 0.03 + 2 * np.spacing(np.abs(a))), (k, np.abs(a - b).max())
