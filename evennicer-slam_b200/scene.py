@@ -33,13 +33,10 @@ def decoder_tensors(decoders, level: str):
 
 def decoder_grad_views(flat: torch.Tensor, params: Sequence[torch.Tensor]):
     """Views of the flat per-decoder gradient buffer, one per parameter (reference shapes)."""
-    out, off = [], 0
-    for p in params:
-        n = p.numel()
-        out.append(flat[off:off + n].view(p.shape))
-        off += n
-    assert off == flat.numel(), (off, flat.numel())
-    return out
+    sizes = [p.numel() for p in params]
+    assert sum(sizes) == flat.numel(), (sum(sizes), flat.numel())
+    # one split call instead of one slice per tensor (69 tensors per mapping step: host time, not GPU time)
+    return [v.view(p.shape) for v, p in zip(flat.split_with_sizes(sizes), params)]
 
 
 def is_native_strided(grid: torch.Tensor) -> bool:

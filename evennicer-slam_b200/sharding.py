@@ -38,47 +38,62 @@ def global_depth_max(local: torch.Tensor, group=None) -> torch.Tensor:
     return local
 
 
-def allreduce_sum_(tensors: Sequence[Optional[torch.Tensor]], group=None, big_bytes: int = 1 << 20) -> None:
-    """In-place SUM all-reduce of gradient tensors.
+def _dense_span(t: torch.Tensor) -> Optional[Tuple[int, int]]:
+    """[lo, hi) storage offsets (in elements) of a tensor that covers a contiguous piece of its storage exactly once --
+    contiguous tensors and permuted views of contiguous buffers (the native-layout grid gradients) -- else None."""
+    if t.numel() == 0:
+        return None
+    dims = sorted(((st, n) for st, n in zip(t.stride(), t.shape) if n > 1))
+    expect = 1
+    for st, n in dims:
+        if st != expect:
+            return None
+        expect *= n
+    return t.storage_offset(), t.storage_offset() + t.numel()
 
-    Large contiguous tensors (the dense grid gradients, 2.7-22 MiB each for room0) are reduced in place, one
-    collective each -- no staging copy; the many small ones (69 decoder tensors, camera tensors) are coalesced
-    into one flat buffer per dtype, one collective, and scattered back.
+
+def allreduce_sum_(tensors: Sequence[Optional[torch.Tensor]], group=None, big_bytes: int = 1 << 20) -> None:
+    """In-place SUM all-reduce of gradient tensors, with as few collectives as the memory layout allows.
+
+    The render backward hands out its gradients as views of ONE zero-filled arena (native-layout grid gradients followed
+    by the flat decoder gradients): tensors that are dense pieces of a shared storage are all-reduced as ONE span of that
+    storage, in place (the sum is elementwise, so the views' permutations do not matter; only a few elements of alignment
+    padding may separate the pieces).  Whatever is left (stand-alone tensors) is reduced in place when large, or
+    coalesced into one flat buffer per dtype when small.
     """
     if world(group)[1] == 1:
         return
-    small = {}
+    by_store = {}
+    loose = []
     for t in tensors:
         if t is None:
             continue
-        if t.is_contiguous() and t.numel() * t.element_size() >= big_bytes:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        sp = _dense_span(t)
+        if sp is None:
+            loose.append(t)
         else:
-            small.setdefault((t.dtype, t.device), []).append(t)
+            by_store.setdefault((t.untyped_storage().data_ptr(), t.dtype, t.device), []).append((sp, t))
+    small = {}
+    for (_, dtype, dev), items in by_store.items():
+        lo = min(sp[0] for sp, _ in items)
+        hi = max(sp[1] for sp, _ in items)
+        covered = sum(sp[1] - sp[0] for sp, _ in items)
+        t0 = items[0][1]
+        # only alignment padding may lie between the pieces (the arena pads every sink to 16 bytes): anything larger could
+        # be somebody else's live data, which an in-place SUM over the span would corrupt
+        if (hi - lo) - covered <= 16 * len(items) and ((hi - lo) * t0.element_size() >= big_bytes or len(items) > 1):
+            span = torch.empty(0, dtype=dtype, device=dev).set_(t0.untyped_storage(), lo, (hi - lo,), (1,))
+            dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
+        else:
+            for _, t in items:
+                small.setdefault((dtype, dev), []).append(t)
+    for t in loose:
+        small.setdefault((t.dtype, t.device), []).append(t)
     for (_, _), ts in small.items():
-        # tensors that are views of ONE storage and cover it densely (the decoder gradients are views of the flat
-        # per-decoder buffers the backward kernel reduced into) are all-reduced as the storage span: no copies
-        by_store = {}
-        for b in ts:
-            by_store.setdefault(b.untyped_storage().data_ptr(), []).append(b)
-        rest = []
-        for _, vs in by_store.items():
-            es = vs[0].element_size()
-            if len(vs) > 1 and all(v.is_contiguous() for v in vs):
-                lo = min(v.storage_offset() for v in vs)
-                hi = max(v.storage_offset() + v.numel() for v in vs)
-                if (hi - lo) <= 2 * sum(v.numel() for v in vs):
-                    span = torch.empty(0, dtype=vs[0].dtype, device=vs[0].device).set_(
-                        vs[0].untyped_storage(), lo, (hi - lo,), (1,))
-                    dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
-                    continue
-            rest.extend(vs)
-        if not rest:
-            continue
-        flat = torch.cat([b.reshape(-1) for b in rest]) if len(rest) > 1 else rest[0].reshape(-1).contiguous()
+        flat = torch.cat([b.reshape(-1) for b in ts]) if len(ts) > 1 else ts[0].reshape(-1).contiguous()
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         off = 0
-        for b in rest:
+        for b in ts:
             b.copy_(flat[off:off + b.numel()].view_as(b))
             off += b.numel()
 

@@ -37,6 +37,27 @@ def _worker(rank, world, port, q):
         sh.allreduce_sum_([v1, v2, v3], big_bytes=1 << 20)
         assert torch.all(v1 == tot) and torch.all(v2 == 2 * tot) and torch.all(v3 == 3 * tot)
         assert torch.all(arena[:4] == 0) and torch.all(arena[30:] == 0)
+        # native-layout grid gradients (permuted views) + flat decoder gradients in one arena -> ONE collective, in place
+        arena2 = torch.zeros(2 * 3 * 4 * 32 + 8 + 20)
+        gridg = arena2[:768].view(2, 3, 4, 32).permute(3, 0, 1, 2).unsqueeze(0)       # [1,32,Z,Y,X] view of [Z,Y,X,32]
+        decg = arena2[776:796].view(4, 5)
+        assert not gridg.is_contiguous() and sh._dense_span(gridg) == (0, 768)
+        gridg.copy_(torch.arange(768.).view(1, 32, 2, 3, 4) * (rank + 1)); decg.fill_(float(rank + 1))
+        calls = []
+        real = dist.all_reduce
+        dist.all_reduce = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+        try:
+            sh.allreduce_sum_([gridg, decg, None], big_bytes=1 << 20)
+        finally:
+            dist.all_reduce = real
+        assert len(calls) == 1
+        assert torch.equal(gridg, torch.arange(768.).view(1, 32, 2, 3, 4) * tot) and torch.all(decg == tot)
+        assert torch.all(arena2[768:776] == 0) and torch.all(arena2[796:] == 0)
+        # a strided (non-dense) tensor falls back to the coalesced copy path and is still reduced correctly
+        base = torch.zeros(6, 4); col = base[:, 1]
+        col.fill_(float(rank + 1))
+        sh.allreduce_sum_([col])
+        assert torch.all(base[:, 1] == tot) and torch.all(base[:, 0] == 0)
         # frame permutation: rank-major padded blocks -> frame order, ragged last batch
         perm, pad = sh._frame_permutation(23, 10, world, "cpu")
         blocks = []
