@@ -163,7 +163,7 @@ def blas_threads():
         return 1
 
 
-def cpu_baseline(budget_s=20.0):
+def cpu_baseline(budget_s=12.0):
     """Bounded sample of the mapping workload on the host cores (kind 'port': numpy oracle)."""
     import torch
     import render_oracle as orc
@@ -177,11 +177,15 @@ def cpu_baseline(budget_s=20.0):
     probe = time.perf_counter() - t0
     rate = n / probe
     n_pf = int(max(10, min(PIX_PER_FRAME, rate * budget_s / N_FRAMES)))
+    # whole batches (new pixel draw each) until about `budget_s` seconds of CPU work have been timed
+    reps = int(max(1, min(40, budget_s * rate / max(n_pf * N_FRAMES, 1))))
     t0 = time.perf_counter()
-    n = oracle_step(sc, frames, n_pf, 1, t32, t64)
+    n = 0
+    for r in range(reps):
+        n += oracle_step(sc, frames, n_pf, 1 + r, t32, t64)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "rays/s", "cores": blas_threads(), "kind": "port",
-            "sample": f"{n} rays ({N_FRAMES} frames x {n_pf} px) of the {N_RAYS}-ray colour-stage mapping batch, "
+            "sample": f"{n} rays = {reps} x ({N_FRAMES} frames x {n_pf} px) of the {N_RAYS}-ray colour-stage mapping batch, "
                       f"fwd+bwd, numpy oracle, {dt:.1f} s", "host_cpus": os.cpu_count()}
 
 
