@@ -470,6 +470,9 @@ def measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world):
         depth, unc, color = renderer.render_batch_ray(grids, decoders, d_rd, d_ro, dev, "color", gt_depth=sd)
         loss = torch.where(sd > 0, torch.abs(sd - depth), 0.0).sum() + 0.2 * torch.abs(sc_ - color).sum()
         loss.backward()
+        if world > 1:      # sharded mapping: the replicated scene's gradients are summed over the ranks, as in the main step
+            from evennicer_slam_b200 import sharding
+            sharding.allreduce_sum_([t.grad for t in list(grids.values()) + params])
         outs.update(depth=depth.detach(), var=unc.detach(), color=color.detach(), g_ro=d_ro.grad, g_rd=d_rd.grad,
                     loss=loss.detach().reshape(1))
         return loss
@@ -507,7 +510,8 @@ def measure_e2e(args, dev, renderer, decoders, grids, frames, scene, world):
             "d2h_bytes_per_step": d2h,
             "timing": "host wall clock around K synchronous steps: pinned H2D copies, "
                       + ("CUDA-graph replay of" if use_graph else "eager") +
-                      " render_batch_ray + loss + backward, D2H copies, stream sync"}
+                      " render_batch_ray + loss + backward" + (" + gradient all-reduce" if world > 1 else "") +
+                      ", D2H copies, stream sync"}
 
 
 def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20):
