@@ -147,6 +147,8 @@ struct TcArgs {
   int64_t n;
   float *out4;            // [n][4]
   int apply_mask;         // last launch of the stage and the caller wants the bound rule
+  int separate;           // 1: write this decoder's own plane (no read-modify-write of a shared raw array): middle
+                          // (inside ? 1 : 0, 0, 0, occ), fine (0, 0, 0, occ), colour (r, g, b, 0) -- combined by composite_kernel
   uint32_t *msave;        // optional: this decoder's saved relu masks, one word per point and block --
                           // [n_tiles32][5][32], word (tile, i, j) = point 32 tile + j, bit k = unit k of block i active
 };
@@ -161,12 +163,11 @@ constexpr int TC_GROUP_COLS = 256, TC_COLS = 512;
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory"); }
 
 template <int LEVEL, int CD, int NO, bool F64>
-__global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
+__device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
   using P = MlpPackTC<CD>;
   constexpr int TC_FL = TC_FH + CD;
   static_assert(TC_FL + CD <= TC_GROUP_COLS, "TMEM budget of a tile group");
   static_assert(P::off_W3e() == P::off_W0() + 32 * EMBP && TC_D3 == TC_D + 32, "[W0; W3e] and [D | D3] must be contiguous");
-  extern __shared__ __align__(128) float smem[];
   float *sw = smem;                                     // the tc blob
   float *stile = smem + P::total() + (threadIdx.x >> 5) * 1024;   // this warp's [32][32] gather staging tile
   __shared__ __align__(8) uint64_t bars[2];
@@ -322,10 +323,16 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
     if (valid) {
       float4 *dst = reinterpret_cast<float4 *>(a.out4) + pt;
       float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (LEVEL == ENS_LEVEL_MIDDLE) v4.w = o[0];
-      else if (LEVEL == ENS_LEVEL_FINE) { v4 = *dst; v4.w = __fadd_rn(o[0], v4.w); }
-      else { v4 = *dst; v4.x = o[0]; v4.y = o[1]; v4.z = o[2]; }
-      if (a.apply_mask && !inside) v4.w = 100.f;
+      if (a.separate) {
+        if (LEVEL == ENS_LEVEL_COLOR) { v4.x = o[0]; v4.y = o[1]; v4.z = o[2]; }
+        else v4.w = o[0];
+        if (LEVEL == ENS_LEVEL_MIDDLE) v4.x = inside ? 1.f : 0.f;
+      } else {
+        if (LEVEL == ENS_LEVEL_MIDDLE) v4.w = o[0];
+        else if (LEVEL == ENS_LEVEL_FINE) { v4 = *dst; v4.w = __fadd_rn(o[0], v4.w); }
+        else { v4 = *dst; v4.x = o[0]; v4.y = o[1]; v4.z = o[2]; }
+        if (a.apply_mask && !inside) v4.w = 100.f;
+      }
       *dst = v4;
     }
     // the next tile's tcgen05.st must not overtake this tile's TMEM loads
@@ -338,11 +345,39 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
   if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"((uint32_t)TC_COLS) : "memory");
 }
 
+template <int LEVEL, int CD, int NO, bool F64>
+__global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  decode_tc_body<LEVEL, CD, NO, F64>(a, smem);
+}
+
+// All decoders of a stage in ONE launch, blockIdx.y = decoder, each writing its own output plane (TcArgs::separate):
+// for small batches (tracking: 9 600 points = 38 CTAs per decoder) three back-to-back launches are three times the
+// latency of one tile chain; side by side they still fit on the 148 SMs.
+struct TcMultiArgs {
+  TcArgs base;
+  float *out[3];
+  uint32_t *msave[3];
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(256, 1) decode_tc_multi_kernel(TcMultiArgs m) {
+  extern __shared__ __align__(128) float smem[];
+  TcArgs a = m.base;
+  const int d = blockIdx.y;
+  a.out4 = m.out[d];
+  a.msave = m.msave[d];
+  a.separate = 1;
+  if (d == 0) decode_tc_body<ENS_LEVEL_MIDDLE, 32, 1, true>(a, smem);
+  else if (d == 1) decode_tc_body<ENS_LEVEL_FINE, 64, 1, true>(a, smem);
+  else if (STAGE == ENS_STAGE_COLOR) decode_tc_body<ENS_LEVEL_COLOR, 32, 4, true>(a, smem);
+}
+
 template <int LEVEL, int CD, int NO>
 static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s,
                             uint32_t *msave = nullptr) {
   TcArgs a;
-  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.separate = 0;
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -401,14 +436,29 @@ __global__ void __launch_bounds__(NT_MMA) place_kernel(DevScene sc, RayArgs ra, 
   }
 }
 
-__global__ void __launch_bounds__(128) composite_kernel(const float4 *__restrict__ raw, const double *__restrict__ z,
+__global__ void __launch_bounds__(128) composite_kernel(float4 *__restrict__ raw, const double *__restrict__ z,
                                                         int64_t R, int S, double *__restrict__ depth,
                                                         double *__restrict__ var, float *__restrict__ color,
-                                                        float *__restrict__ w_out) {
+                                                        float *__restrict__ w_out, const float4 *__restrict__ planes,
+                                                        int n_planes) {
   const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= R) return;
-  const float4 *rr = raw + ray * S;
+  float4 *rr = raw + ray * S;
   const double *zz = z + ray * S;
+  if (planes != nullptr) {
+    // the decoders wrote separate planes (decode_tc_multi_kernel): raw = (rgb of the colour decoder, fine_occ + middle_occ),
+    // occupancy 100 outside the bound (Renderer.py:58) -- the same values the sequential launches leave in `raw`
+    const int64_t P = R * (int64_t)S;
+    for (int k = 0; k < S; ++k) {
+      const int64_t pi = ray * S + k;
+      const float4 m = planes[pi];
+      float4 r4 = make_float4(0.f, 0.f, 0.f, m.w);
+      if (n_planes > 1) r4.w = __fadd_rn(planes[P + pi].w, m.w);
+      if (n_planes > 2) { const float4 c4 = planes[2 * P + pi]; r4.x = c4.x; r4.y = c4.y; r4.z = c4.z; }
+      if (m.x == 0.f) r4.w = 100.f;
+      rr[k] = r4;
+    }
+  }
   float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
   double dep = 0.0;
   for (int k = 0; k < S; ++k) {                       // sequential cumprod / sums, exactly the fused kernels' order
@@ -434,9 +484,92 @@ __global__ void __launch_bounds__(128) composite_kernel(const float4 *__restrict
   color[ray * 3 + 0] = cr; color[ray * 3 + 1] = cg; color[ray * 3 + 2] = cb;
 }
 
+// The same compositing for SMALL batches (tracking: 200 rays would be two CTAs of the kernel above, every thread walking
+// 48 dependent global loads three times): one warp per ray.  The lanes fetch and combine the samples and evaluate the
+// sigmoids in parallel into shared memory; lane 0 then runs the sequential products and sums in exactly the order of
+// the kernel above (bit-identical results); the lanes write the weights back.
+__global__ void __launch_bounds__(128) composite_warp_kernel(float4 *__restrict__ raw, const double *__restrict__ z,
+                                                             int64_t R, int S, double *__restrict__ depth,
+                                                             double *__restrict__ var, float *__restrict__ color,
+                                                             float *__restrict__ w_out, const float4 *__restrict__ planes,
+                                                             int n_planes) {
+  __shared__ float4 s_raw[4][ENS_MAX_SAMPLES];
+  __shared__ double s_z[4][ENS_MAX_SAMPLES];
+  __shared__ float s_a[4][ENS_MAX_SAMPLES];
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + wi;
+  if (ray >= R) return;
+  const int64_t P = R * (int64_t)S;
+  for (int k = lane; k < S; k += 32) {
+    const int64_t pi = ray * S + k;
+    float4 r4;
+    if (planes != nullptr) {
+      const float4 m = planes[pi];
+      r4 = make_float4(0.f, 0.f, 0.f, m.w);
+      if (n_planes > 1) r4.w = __fadd_rn(planes[P + pi].w, m.w);
+      if (n_planes > 2) { const float4 c4 = planes[2 * P + pi]; r4.x = c4.x; r4.y = c4.y; r4.z = c4.z; }
+      if (m.x == 0.f) r4.w = 100.f;
+      raw[pi] = r4;
+    } else {
+      r4 = raw[pi];
+    }
+    s_raw[wi][k] = r4;
+    s_z[wi][k] = z[pi];
+    s_a[wi][k] = 1.f / (1.f + expf(-(10.f * r4.w)));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    double dep = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const float4 rk = s_raw[wi][k];
+      const float alpha = s_a[wi][k];
+      const float wk = __fmul_rn(alpha, T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f));
+      dep = __dadd_rn(dep, __dmul_rn((double)wk, s_z[wi][k]));
+      cr = __fadd_rn(cr, __fmul_rn(wk, rk.x)); cg = __fadd_rn(cg, __fmul_rn(wk, rk.y)); cb = __fadd_rn(cb, __fmul_rn(wk, rk.z));
+      s_a[wi][k] = wk;                                  // alpha is not needed again: keep the weight
+    }
+    double v = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const double tmp = __dsub_rn(s_z[wi][k], dep);
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn((double)s_a[wi][k], tmp), tmp));
+    }
+    depth[ray] = dep;
+    var[ray] = v;
+    color[ray * 3 + 0] = cr; color[ray * 3 + 1] = cg; color[ray * 3 + 2] = cb;
+  }
+  __syncwarp();
+  if (w_out)
+    for (int k = lane; k < S; k += 32) w_out[ray * S + k] = s_a[wi][k];
+}
+
 int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage) {
   if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
-  return n_rays * (int64_t)S * (24 + 8 + 16);
+  return n_rays * (int64_t)S * (24 + 8 + 16 + 3 * 16);      // points, z, raw, one output plane per decoder
+}
+
+static bool use_tc_multi() {
+  const char *v = std::getenv("ENS_TC_MULTI");
+  return !(v && v[0] == '0');
+}
+
+template <int STAGE>
+static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P, float *planes, cudaStream_t s, int sms) {
+  constexpr int ndec = (STAGE == ENS_STAGE_FINE) ? 2 : 3;
+  TcMultiArgs m;
+  m.base.sc = a.sc; m.base.pts = pts; m.base.n = P; m.base.out4 = nullptr; m.base.apply_mask = 0; m.base.msave = nullptr;
+  m.base.separate = 1;
+  for (int d = 0; d < 3; ++d) {
+    m.out[d] = planes + (int64_t)d * P * 4;
+    m.msave[d] = a.save_masks ? a.save_masks + (int64_t)d * a.n_tiles * 160 : nullptr;
+  }
+  const size_t smem = (size_t)(MlpPackTC<64>::total() + 8 * 1024) * 4;       // the fine decoder's blob is the largest
+  if (cudaFuncSetAttribute(decode_tc_multi_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  const int64_t pairs = ((P + 127) / 128 + 1) / 2;
+  decode_tc_multi_kernel<STAGE><<<dim3((unsigned)pairs, ndec), 256, smem, s>>>(m);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
 }
 
 int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s) {
@@ -451,10 +584,32 @@ int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, c
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   place_kernel<<<g, NT_MMA, 0, s>>>(a.sc, a.ra, z, pts);
   ENS_CHECK_CUDA();
-  const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s, a.save_masks, a.n_tiles * 160);
-  if (rc != ENS_OK) return rc;
-  composite_kernel<<<(unsigned)((a.ra.R + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float4 *>(raw), z, a.ra.R, a.ra.S,
-                                                                    a.depth, a.var, a.color, a.w_out);
+  // small batch: every decoder of the stage side by side in one launch (all CTAs resident at once), outputs combined by
+  // the compositing kernel; otherwise one launch per decoder
+  const float4 *planes = nullptr;
+  int n_planes = 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
+  const int64_t pairs = ((P + 127) / 128 + 1) / 2;
+  if (ndec > 1 && pairs * ndec <= sms && use_tc_multi()) {
+    float *pl = reinterpret_cast<float *>(base + P * 48);
+    const int rc = stage == ENS_STAGE_FINE ? launch_decode_tc_multi<ENS_STAGE_FINE>(a, pts, P, pl, s, sms)
+                                           : launch_decode_tc_multi<ENS_STAGE_COLOR>(a, pts, P, pl, s, sms);
+    if (rc != ENS_OK) return rc;
+    planes = reinterpret_cast<const float4 *>(pl);
+    n_planes = ndec;
+  } else {
+    const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s, a.save_masks, a.n_tiles * 160);
+    if (rc != ENS_OK) return rc;
+  }
+  if (a.ra.R <= 4096 && a.ra.S <= ENS_MAX_SAMPLES)
+    composite_warp_kernel<<<(unsigned)((a.ra.R + 3) / 4), 128, 0, s>>>(reinterpret_cast<float4 *>(raw), z, a.ra.R, a.ra.S,
+                                                                       a.depth, a.var, a.color, a.w_out, planes, n_planes);
+  else
+    composite_kernel<<<(unsigned)((a.ra.R + 127) / 128), 128, 0, s>>>(reinterpret_cast<float4 *>(raw), z, a.ra.R, a.ra.S,
+                                                                      a.depth, a.var, a.color, a.w_out, planes, n_planes);
   ENS_CHECK_CUDA();
   return ENS_OK;
 }

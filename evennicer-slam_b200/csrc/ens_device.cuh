@@ -215,6 +215,8 @@ struct BwdArgs {
   const float *save_h;          // from the forward (null: recompute when decoder grads are wanted)
   int64_t n_tiles;
   int mask_fmt;                 // 0: words in the mma kernels' lane layout; 1: one word per point (tcgen05 forward)
+  int dec_par;                  // 1: blockIdx.y selects ONE decoder of the stage (small pose-only batches: 3x the CTAs,
+                                //    a third of the per-CTA latency); ray gradients are then accumulated atomically
   const float *raw;
   const double *g_depth, *g_var;
   const float *g_color;

@@ -772,11 +772,15 @@ render_bwd_mma_kernel(BwdArgs a) {
     dst[1] = make_float4(pn[0], pn[1], pn[2], 0.f);
   }
 
+  // decoder-parallel mode (pose-only saved path, small batches): this CTA runs only decoder blockIdx.y of the stage
+  constexpr bool DP_OK = !WG && !RECOMP && !SPLIT;
+  const int dsel = (DP_OK && a.dec_par) ? (int)blockIdx.y : -1;
   const float go1[1] = {g_occ};
-  decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
-  if (STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR)
+  if (dsel < 0 || dsel == 0)
+    decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_MIDDLE, 32, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
+  if ((STAGE == ENS_STAGE_FINE || STAGE == ENS_STAGE_COLOR) && (dsel < 0 || dsel == 1))
     decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_FINE, 64, 1>(a, sw, w, pn, p32, go1, valid, want_rays, gp);
-  if (STAGE == ENS_STAGE_COLOR) {
+  if (STAGE == ENS_STAGE_COLOR && (dsel < 0 || dsel == 2)) {
     const float go4[4] = {g_rgb[0], g_rgb[1], g_rgb[2], 0.f};            // output 3 is overwritten (decoder.py:341)
     decoder_bwd_mma<STAGE, WG, RECOMP, SPLIT, ENS_LEVEL_COLOR, 32, 4>(a, sw, w, pn, p32, go4, valid, want_rays, gp);
   }
@@ -796,8 +800,13 @@ render_bwd_mma_kernel(BwdArgs a) {
         so += gk;
         sd += gk * zz[base + k];
       }
-      if (a.g_rays_o) a.g_rays_o[ray * 3 + s] = (float)so;
-      if (a.g_rays_d) a.g_rays_d[ray * 3 + s] = (float)sd;
+      if (dsel >= 0) {            // one of up to three CTAs of this ray: accumulate (the launcher zeroed the buffers)
+        if (a.g_rays_o) atomicAdd(a.g_rays_o + ray * 3 + s, (float)so);
+        if (a.g_rays_d) atomicAdd(a.g_rays_d + ray * 3 + s, (float)sd);
+      } else {
+        if (a.g_rays_o) a.g_rays_o[ray * 3 + s] = (float)so;
+        if (a.g_rays_d) a.g_rays_d[ray * 3 + s] = (float)sd;
+      }
     }
   }
 }
@@ -1020,6 +1029,11 @@ __global__ void __launch_bounds__(256, 2) wgrad_split_kernel(WgradArgs a) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+static bool use_decoder_parallel() {
+  const char *v = std::getenv("ENS_BWD_DECODER_PARALLEL");
+  return !(v && v[0] == '0');
+}
+
 template <int STAGE, bool WG, bool RECOMP, bool SPLIT>
 static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
   using CFG = BwdCfg<STAGE, WG, RECOMP, SPLIT>;
@@ -1028,7 +1042,20 @@ static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
   if (cudaFuncSetAttribute(render_bwd_mma_kernel<STAGE, WG, RECOMP, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return ENS_ECUDA;
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
-  render_bwd_mma_kernel<STAGE, WG, RECOMP, SPLIT><<<g, CFG::NT, smem, s>>>(a);
+  unsigned gy = 1;
+  a.dec_par = 0;
+  if (!WG && !RECOMP && !SPLIT && use_decoder_parallel()) {
+    // small pose-only batches (tracking: 200 rays = 50 CTAs) leave most SMs idle and are bound by the latency of one CTA
+    // walking its decoders in turn: give every decoder its own CTA while all of them still fit in one wave
+    constexpr int ndec = (STAGE == ENS_STAGE_MIDDLE) ? 1 : (STAGE == ENS_STAGE_FINE ? 2 : 3);
+    if (ndec > 1 && (int64_t)g * ndec <= 296) {
+      a.dec_par = 1;
+      gy = ndec;
+      if (a.g_rays_o && cudaMemsetAsync(a.g_rays_o, 0, sizeof(float) * 3 * a.ra.R, s) != cudaSuccess) return ENS_ECUDA;
+      if (a.g_rays_d && cudaMemsetAsync(a.g_rays_d, 0, sizeof(float) * 3 * a.ra.R, s) != cudaSuccess) return ENS_ECUDA;
+    }
+  }
+  render_bwd_mma_kernel<STAGE, WG, RECOMP, SPLIT><<<dim3(g, gy), CFG::NT, smem, s>>>(a);
   ENS_CHECK_CUDA();
   return ENS_OK;
 }

@@ -44,8 +44,8 @@ def test_sizes_match_reference_parameter_counts(built):
     assert L.ens_fwd_saved_bytes(1000, 48, 3, 1) == 3 * 1500 * 5 * 128 + 3 * 1500 * 5 * 4096
     assert L.ens_fwd_saved_bytes(1000, 48, 0, 1) == 0            # coarse stage: FFMA kernels, nothing saved
     assert L.ens_fwd_saved_bytes(1000, 40, 3, 1) == 0            # 40 samples per ray do not tile the CTAs
-    # forward-only scratch: points f64[3] + z f64 + raw f32[4] per sample point
-    assert L.ens_fwd_scratch_bytes(1000, 48, 3) == 48000 * 48 and L.ens_fwd_scratch_bytes(1000, 48, 0) == 0
+    # tcgen05-path scratch: points f64[3] + z f64 + raw f32[4] + one f32[4] output plane per decoder, per sample point
+    assert L.ens_fwd_scratch_bytes(1000, 48, 3) == 48000 * 96 and L.ens_fwd_scratch_bytes(1000, 48, 0) == 0
     import evennicer_slam_b200.synthetic as syn
     for li, lv in enumerate(syn.LEVELS):
         n = sum(int(np.prod(s)) for _, s in syn.decoder_param_shapes(lv))
