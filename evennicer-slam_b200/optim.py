@@ -109,7 +109,7 @@ class FrustumGridAdam:
 
 class FusedAdam:
     """``torch.optim.Adam`` for the small parameter groups of the reference's optimizers (decoder weights, camera tensors;
-    Mapper.py:396-423, Tracker.py:326-333) as ONE launch per step (``ens_tensors_adam_step``).
+    Mapper.py:396-423, Tracker.py:335-342) as ONE launch per step (``ens_tensors_adam_step``).
 
     Mirrors the part of the torch API the reference uses: ``FusedAdam([{'params': [...], 'lr': 0}, ...])``,
     ``opt.param_groups[i]['lr'] = ...``, ``opt.step()``, ``opt.zero_grad()``; default betas / eps, no weight decay, no

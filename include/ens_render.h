@@ -211,7 +211,7 @@ int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double bet
                        int64_t step, const double *dyn, int clear_grad, ens_stream_t stream);
 
 /* Adam over many small tensors in ONE launch: the other parameter groups of the mapper's optimizer (decoder weights,
- * camera tensors; src/Mapper.py:396-423, :625) and the tracker's camera tensor (src/Tracker.py:326-333).  Same
+ * camera tensors; src/Mapper.py:396-423, :625) and the tracker's camera tensor (src/Tracker.py:335-342).  Same
  * arithmetic as ens_grid_adam_step.  params_host / grads_host / sizes_host / groups_host: host arrays of n_tensors device
  * pointers, element counts and group indices; lrs_host[n_groups] (n_groups <= 8); exp_avg / exp_avg_sq: device float
  * buffers of sum(sizes) elements, tensor i at the sum of the sizes before it, zero-initialised by the caller.
