@@ -84,3 +84,33 @@ def test_render_path_fails_loudly_without_cuda():
     decoders, c, renderer, cfg = harness.build(scene, "cpu")
     with pytest.raises((RuntimeError, ValueError)):
         renderer.render_batch_ray(c, decoders, torch.zeros(4, 3), torch.zeros(4, 3), "cpu", "color")
+
+
+def test_host_wrappers_refuse_cpu_tensors():
+    """No CPU fallback anywhere on the product path: the optimiser / loss wrappers raise on CPU tensors instead of
+    computing something in torch."""
+    import pytest
+    import torch
+    from evennicer_slam_b200 import losses, optim
+    g = torch.zeros(1, 32, 2, 3, 4)
+    with pytest.raises(ValueError):
+        optim.FrustumGridAdam({"grid_fine": g}, None)
+    with pytest.raises(ValueError):
+        optim.FusedAdam([torch.zeros(3, requires_grad=True)])
+    with pytest.raises(RuntimeError):
+        losses.event_loss(torch.zeros(20, 30, 2), torch.zeros(20, 30, 2))
+    with pytest.raises(RuntimeError):
+        losses.mapper_loss(torch.zeros(4), torch.zeros(4, 3), torch.zeros(4, dtype=torch.float64), torch.zeros(4, 3))
+    with pytest.raises(RuntimeError):
+        losses.tracker_loss(torch.zeros(4), torch.zeros(4, 3), torch.zeros(4, dtype=torch.float64),
+                            torch.zeros(4, dtype=torch.float64), torch.zeros(4, 3))
+
+
+def test_gaussian_kernel_matches_torchvision_default_sigma():
+    import numpy as np
+    import torch
+    from torchvision.transforms import _functional_tensor as FT
+    from evennicer_slam_b200.losses import gaussian_kernel1d
+    for ks in (3, 9, 15):
+        want = FT._get_gaussian_kernel1d(ks, ks * 0.15 + 0.35, torch.float32, torch.device("cpu")).numpy()
+        assert np.array_equal(gaussian_kernel1d(ks), want)
