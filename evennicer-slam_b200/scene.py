@@ -25,10 +25,28 @@ from . import _lib
 from ._lib import LEVELS, STAGE_LEVELS, EnsScene
 
 
+_PARAM_SLOTS = weakref.WeakKeyDictionary()     # decoder module -> [(owning submodule's _parameters dict, name)], state_dict order
+
+
 def decoder_tensors(decoders, level: str):
-    """Parameters of one decoder in state_dict order (the order ens_pack_decoder expects)."""
+    """Parameters of one decoder in state_dict order (the order ens_pack_decoder expects).
+
+    The module tree is walked once per decoder object (``named_parameters`` costs ~70 us per decoder, three times per
+    render call); afterwards the live ``_parameters`` dicts are read directly, so a Parameter that was re-assigned, moved
+    by ``.to()`` or loaded by ``load_state_dict`` is still picked up."""
     dec = getattr(decoders, level + "_decoder")
-    return [p for _, p in dec.named_parameters()]
+    slots = _PARAM_SLOTS.get(dec)
+    if slots is None:
+        slots = []
+        for mod_name, mod in dec.named_modules():
+            for name, p in mod._parameters.items():
+                if p is not None:
+                    slots.append((mod._parameters, name))
+        # named_modules / _parameters iterate in registration order, which is named_parameters' (= state_dict) order
+        ref = [p for _, p in dec.named_parameters()]
+        assert len(ref) == len(slots) and all(d[n] is p for (d, n), p in zip(slots, ref))
+        _PARAM_SLOTS[dec] = slots
+    return [d[n] for d, n in slots]
 
 
 def decoder_grad_views(flat: torch.Tensor, params: Sequence[torch.Tensor]):
@@ -156,16 +174,31 @@ class SceneCache:
         return packed
 
 
+_BOUND_CACHE: Dict[int, tuple] = {}
+
+
+def _bound_floats(bound: torch.Tensor):
+    """The six floats of a (3,2) bound tensor, read once per tensor object and version (two reads per render call before)."""
+    e = _BOUND_CACHE.get(id(bound))
+    if e is not None and e[0]() is bound and e[1] == bound._version:
+        return e[2]
+    vals = tuple(float(x) for x in bound.detach().to("cpu", torch.float64).reshape(-1))
+    if len(_BOUND_CACHE) > 64:
+        _BOUND_CACHE.clear()
+    _BOUND_CACHE[id(bound)] = (weakref.ref(bound), bound._version, vals)
+    return vals
+
+
 def build_scene_struct(bound: torch.Tensor, coarse_bound: torch.Tensor,
                        native_grids: Dict[str, torch.Tensor], packed: Dict[str, torch.Tensor]) -> EnsScene:
     """Fill the C struct.  ``bound`` values are read on the host (they are CPU float64 in the
     reference: EvenNICER_SLAM.py:170-175)."""
     sc = EnsScene()
-    b = bound.detach().to("cpu", torch.float64)
-    cb = coarse_bound.detach().to("cpu", torch.float64)
+    b = _bound_floats(bound)
+    cb = _bound_floats(coarse_bound)
     for k in range(3):
-        sc.bound[k][0], sc.bound[k][1] = float(b[k, 0]), float(b[k, 1])
-        sc.coarse_bound[k][0], sc.coarse_bound[k][1] = float(cb[k, 0]), float(cb[k, 1])
+        sc.bound[k][0], sc.bound[k][1] = b[2 * k], b[2 * k + 1]
+        sc.coarse_bound[k][0], sc.coarse_bound[k][1] = cb[2 * k], cb[2 * k + 1]
     for li, lv in enumerate(LEVELS):
         g = native_grids.get(lv)
         if g is not None:

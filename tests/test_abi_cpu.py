@@ -114,3 +114,31 @@ def test_gaussian_kernel_matches_torchvision_default_sigma():
     for ks in (3, 9, 15):
         want = FT._get_gaussian_kernel1d(ks, ks * 0.15 + 0.35, torch.float32, torch.device("cpu")).numpy()
         assert np.array_equal(gaussian_kernel1d(ks), want)
+
+
+def test_decoder_tensors_cache_follows_the_live_parameters():
+    """scene.decoder_tensors walks the module tree once per decoder object and then reads the live _parameters dicts:
+    state_dict order, and re-assigned / loaded / copied parameters are still the ones returned."""
+    import copy
+    import torch
+    from evennicer_slam_b200.decoder import NICE
+    from evennicer_slam_b200.scene import decoder_tensors, _bound_floats
+    m = NICE(coarse=True)
+    for lv in ("coarse", "middle", "fine", "color"):
+        dec = getattr(m, lv + "_decoder")
+        want = [p for _, p in dec.named_parameters()]
+        for _ in range(2):                                   # second call: cached slots
+            got = decoder_tensors(m, lv)
+            assert len(got) == len(want) and all(a is b for a, b in zip(got, want))
+    m.load_state_dict(copy.deepcopy(m.state_dict()))         # in-place copy: same objects
+    assert all(a is b for a, b in zip(decoder_tensors(m, "fine"), [p for _, p in m.fine_decoder.named_parameters()]))
+    new = torch.nn.Parameter(torch.zeros_like(m.fine_decoder.output_linear.bias))
+    m.fine_decoder.output_linear.bias = new                  # a re-assigned Parameter is picked up
+    assert decoder_tensors(m, "fine")[-1] is new
+    m2 = copy.deepcopy(m)                                    # a copy has its own parameters
+    assert all(a is b for a, b in zip(decoder_tensors(m2, "color"), [p for _, p in m2.color_decoder.named_parameters()]))
+    assert not any(a is b for a, b in zip(decoder_tensors(m2, "color"), decoder_tensors(m, "color")))
+    b = torch.tensor([[-1.0, 2.0], [-3.0, 4.0], [-5.0, 6.5]], dtype=torch.float64)
+    assert _bound_floats(b) == (-1.0, 2.0, -3.0, 4.0, -5.0, 6.5)
+    b[2, 1] = 7.0                                            # in-place edit bumps the version
+    assert _bound_floats(b)[-1] == 7.0
