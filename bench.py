@@ -368,6 +368,12 @@ def run_gpu_arm(args):
         eager_ms = sum(a.elapsed_time(b) for a, b in evs2) / args.steps
     launches_timed = TIMER.launches
     ksum = TIMER.summary()
+    # the timed region is ~K x 0.6 ms, shorter than one nvidia-smi sampling period: keep the same load (untimed runs of the
+    # same step) going for ~0.5 s more so the clocks line holds several samples taken UNDER this load.  A fixed count on
+    # EVERY rank: the step contains collectives when world > 1.
+    for _ in range(600 if use_graph else 60):
+        run_step()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
