@@ -6,7 +6,6 @@ PyTorch: autograd finishes the pose gradient from ``d c2w``
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from .functional import _LatticeRays, _SampleRays, _c2w_dev

@@ -6,9 +6,7 @@ Mirrors what ``EvenNICER_SLAM.__init__`` does for the hot path (EvenNICER_SLAM.p
 from __future__ import annotations
 
 import types
-from typing import Dict
 
-import numpy as np
 import torch
 
 from . import synthetic as syn

@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
 from .common import get_rays, get_rays_rescale
 from .functional import RenderSetup, eval_points as _eval_points, render_batch_ray as _render_batch_ray
 from .scene import SceneCache

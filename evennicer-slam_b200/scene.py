@@ -17,12 +17,12 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import LEVELS, STAGE_LEVELS, EnsScene
+from ._lib import LEVELS, EnsScene
 
 
 _PARAM_SLOTS = weakref.WeakKeyDictionary()     # decoder module -> [(owning submodule's _parameters dict, name)], state_dict order

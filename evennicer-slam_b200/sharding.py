@@ -12,7 +12,7 @@ NCCL over NVLink on the GPU box; the same code runs on gloo/CPU tensors in the t
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
