@@ -70,6 +70,52 @@ def _worker(rank, world, port, q):
             blocks.append(rows + [-1] * (pad - len(rows)))
         flat = torch.tensor([x for b in blocks for x in b])
         assert torch.equal(flat[perm], torch.arange(23))
+        # render_frame_sharded end to end on gloo, with the CUDA render replaced by a per-ray CPU stand-in: every
+        # reference batch split over the ranks, the batch's depth maxima taken from the WHOLE batch, one gather per output
+        from evennicer_slam_b200 import functional as fn
+
+        class FakeRenderer:
+            ray_batch_size = 10
+
+            def _setup(self, stage, decoders, device):
+                return stage
+
+        def fake_depth_max(gd):
+            return torch.stack([(gd * 1.2).max().double(), gd.max().double()])
+
+        def fake_render(setup, c, decoders, rd, ro, gd, depth_max=None):
+            # depends on the ray AND on the batch maxima, as sample placement does
+            base = ro[:, 0].double() * 3.0 + rd[:, 1].double()
+            far = depth_max[0] if depth_max is not None else torch.tensor(0.0, dtype=torch.float64)
+            return base + far, base * 0.5 + (depth_max[1] if depth_max is not None else 0.0), \
+                torch.stack([ro[:, 0], rd[:, 0], ro[:, 1] + rd[:, 2]], -1).float()
+        real = (fn.depth_batch_max, fn.render_batch_ray)
+        fn.depth_batch_max, fn.render_batch_ray = fake_depth_max, fake_render
+        try:
+            g0 = torch.Generator().manual_seed(11)
+            n = 37                                                  # 3 full batches of 10 and a ragged one of 7
+            ro_f, rd_f = torch.randn(n, 3, generator=g0), torch.randn(n, 3, generator=g0)
+            gdepth = torch.rand(n, generator=g0) + 0.5
+            got = sh.render_frame_sharded(FakeRenderer(), None, None, rd_f, ro_f, "cpu", "color", gt_depth=gdepth)
+            want = [[], [], []]
+            for i in range(0, n, 10):
+                dm = fake_depth_max(gdepth[i:i + 10])
+                out = fake_render(None, None, None, rd_f[i:i + 10], ro_f[i:i + 10], gdepth[i:i + 10], depth_max=dm)
+                for k in range(3):
+                    want[k].append(out[k])
+            for k in range(3):
+                assert torch.equal(got[k], torch.cat(want[k])), k
+            got_nd = sh.render_frame_sharded(FakeRenderer(), None, None, rd_f, ro_f, "cpu", "coarse", gt_depth=gdepth)
+            assert torch.equal(got_nd[2], torch.cat(want[2]))       # stage coarse ignores gt_depth (Renderer.py:89-93)
+        finally:
+            fn.depth_batch_max, fn.render_batch_ray = real
+        # eval_points_sharded (mesh lattice, config 5): points split over the ranks, outputs gathered in order
+        class FakeEval:
+            def eval_points(self, p, decoders, c, stage, device):
+                return torch.cat([p * 2.0, p.sum(-1, keepdim=True)], -1)
+        pts = torch.arange(13 * 3, dtype=torch.float32).view(13, 3)
+        out = sh.eval_points_sharded(FakeEval(), pts, None, None, "fine", "cpu")
+        assert torch.equal(out, torch.cat([pts * 2.0, pts.sum(-1, keepdim=True)], -1))
         # ragged all-gather
         rows = torch.arange(lo, hi, dtype=torch.float32)[:, None].repeat(1, 3)
         counts = [sh.shard_range(11, r, world)[1] - sh.shard_range(11, r, world)[0] for r in range(world)]
