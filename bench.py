@@ -163,9 +163,25 @@ def blas_threads():
         return 1
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core it can."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)            # BLAS / OpenMP pools numpy already initialised
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+
+
 def cpu_baseline(budget_s=12.0):
     """Bounded sample of the mapping workload on the host cores (kind 'port': numpy oracle)."""
     import torch
+    use_all_host_threads()
     import render_oracle as orc
     scene, frames = make_inputs()
     sc = orc.OracleScene.from_synthetic(scene)
@@ -194,6 +210,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     import render_oracle as orc
     scene, frames = make_inputs()
     sc = orc.OracleScene.from_synthetic(scene)
