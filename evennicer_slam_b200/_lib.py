@@ -2,7 +2,7 @@
 
 There is no fallback: if the shared library is missing or fails to load, importing a
 compute entry point raises.  The library is built in-tree by ``__graft_entry__.build()``
-(``make -C evennicer-slam_b200/csrc``).
+(``make -C evennicer_slam_b200/csrc``).
 """
 from __future__ import annotations
 
@@ -105,7 +105,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(make -C evennicer-slam_b200/csrc). There is no CPU or PyTorch fallback for the render path.")
+                "(make -C evennicer_slam_b200/csrc). There is no CPU or PyTorch fallback for the render path.")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here = header/library mismatch

@@ -17,7 +17,7 @@
 //   * output layer on the FMA pipe (Wo r_4 + Mo c + bo'), read-modify-write of the output row.
 // Two tiles are in flight per CTA (two groups of four warps with their own TMEM columns and barriers).
 // Completion of each MMA batch is tracked with tcgen05.commit -> mbarrier; thread sync around TMEM stores uses
-// tcgen05.wait::st + tcgen05.fence + bar.sync.  Verified first in isolation by scratch/tc_probe.cu.
+// tcgen05.wait::st + tcgen05.fence + bar.sync.  Verified first in isolation by tools/tc_probe.cu.
 #include "ens_mma.cuh"
 
 namespace ens {

@@ -4,7 +4,7 @@
  * The reference has no FFI layer: its seam is the Python call signatures of
  * Renderer / NICE / get_samples.  Each entry point below names the
  * reference function whose body it replaces (paths relative to /root/reference).
- * The Python drop-ins in evennicer-slam_b200/ bind these with ctypes; INTEGRATION.md
+ * The Python drop-ins in evennicer_slam_b200/ bind these with ctypes; INTEGRATION.md
  * shows the stub a maintainer adds on the reference side.
  *
  * Conventions

@@ -427,7 +427,7 @@ def test_room0_mapping_batch_vs_golden_and_oracle():
                 # gradient mass sits in the few samples per ray where alpha(1-alpha) is not ~0, so ONE relu decision
                 # taken on the other side of the kink (|u| < 1e-6, within fp32 rounding of zero) shows as a few 1e-4
                 # in every tensor below that layer: measured 1.9e-4 for the serial-fp32 FFMA kernels and 1.2e-3 for
-                # the tensor-core kernels vs. the CPU reference (scratch/diag_room0.py), all other tensors 1e-6.
+                # the tensor-core kernels vs. the CPU reference (tools/diag_room0.py), all other tensors 1e-6.
                 # Kink-free cases (tiny goldens, cases.TINY_RELU_MARGIN) are held to TOL_GRAD everywhere.
                 assert rel_err(p.grad.cpu().numpy(), ref) < TOL_GRAD_KINK, (name, key)
         gk = "grid_" + name

@@ -38,7 +38,7 @@ ts, te = sum(samp.values()), sum(ex.values())
 src = {}
 def getline(f, ln):
     import os
-    for d in ('evennicer-slam_b200/csrc/', ''):
+    for d in ('evennicer_slam_b200/csrc/', ''):
         p = d + f
         if os.path.exists(p):
             if p not in src: src[p] = open(p).read().splitlines()
