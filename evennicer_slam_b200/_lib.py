@@ -19,7 +19,7 @@ STAGE_LEVELS = {"coarse": ("coarse",), "middle": ("middle",), "fine": ("middle",
                 "color": ("middle", "fine", "color")}
 
 ENS_OK = 0
-ABI_VERSION = 4            # include/ens_render.h: ENS_ABI_VERSION
+ABI_VERSION = 5            # include/ens_render.h: ENS_ABI_VERSION
 
 
 class EnsScene(C.Structure):
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "ens_decoder_num_tensors": (C.c_int, [C.c_int]),
     "ens_bwd_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "ens_fwd_saved_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+    "ens_fwd_saved_bytes_kind": (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "ens_fwd_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "ens_grid_to_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ens_grid_from_native": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),

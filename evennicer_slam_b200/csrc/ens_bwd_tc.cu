@@ -1,0 +1,771 @@
+// Renderer.render_batch_ray BACKWARD on the 5th-generation tensor cores (tcgen05 / UMMA, accumulators in TMEM):
+// autograd of /root/reference/src/utils/Renderer.py:64-199 + src/conv_onet/models/decoder.py:177-203, 312-342 +
+// src/common.py:256-297, stages middle / fine / color.
+//
+//   place_kernel          sample placement (float64, the fused kernels' code)           -> z [R][S], points [R*S][3] f64
+//   composite_bwd_kernel  raw2outputs_nerf_color backward, one warp per ray             -> g_out [R*S][4] = (g_rgb, g_occ)
+//   bwd_tc_kernel         one persistent CTA per SM, blockIdx.y = ROLE (a decoder), 128-point tiles, thread = point = TMEM lane:
+//       data gradients    g_h_{i-1} = g_u_i Wh_i,  g_c += g_u_i M_{i-1},  g_e += g_u_{0,3} W_{0,3e}
+//                         TS form: A = g_u (value + TF32 remainder) written to TMEM with tcgen05.st, B = the transposed
+//                         matrices of MlpPackTCB in shared memory (K-major), 3xTF32, M = 128 points;
+//       weight gradients  S_i = sum_pt g_u_i^T r_{i-1},  Q_i = sum_pt g_u_i^T c,  E_i = sum_pt g_u_i^T e   (K = the POINTS)
+//                         SS form, both operands MN-major (SWIZZLE_128B_BASE32B): every thread stages its rows of
+//                         [r_{i-1} | c] (or Fourier chunks) and of g_u, value and remainder.  The four 32-column blocks
+//                         [x_hi | c_hi | x_lo | c_lo] are ONE M = 128 operand, so the TMEM lanes 64..127 of an accumulator
+//                         hold the remainder products and two passes (B = g_hi, B = g_lo) give the 3xTF32 sum.  The
+//                         accumulators stay in TMEM for ALL tiles of the CTA and are flushed once (RED.ADD) at the end;
+//       tail              trilinear backward (8 lanes per 128-byte voxel line, red.global.add.v4.f32) and coordinate
+//                         gradient, Fourier backward, d L / d p of the point.
+//   unfold_kernel         the sums above are those of the FOLDED network the tcgen05 forward evaluates (r_i = relu(u_i),
+//                         feature injection folded into the next block); by linearity the reference's parameter gradients are
+//                             dW_i   = S_i + Q_i Wc_{i-1}^T + b^_i bc_{i-1}^T        dWc_i = Wh_{i+1}^T Q_{i+1}
+//                             dbc_i  = Wh_{i+1}^T b^_{i+1}                           dWo   = (sum g_out^T r_4) + Qo Wc_4^T + dbo bc_4^T
+//                         -- a few 32x32 products per decoder, one tiny launch.
+//   rays_reduce_kernel    g_o = sum_s g_p, g_d = sum_s z_s g_p
+//
+// Nothing per-point crosses HBM between the data-gradient and the weight-gradient GEMMs (no g_h scratch): what the
+// backward reads per point is what the forward saved -- the relu outputs r_0..r_4 (decoder gradients wanted: saved kind 3)
+// or one mask word per block (pose only: saved kind 2).
+// Roles: the fine decoder's feature vector is 64 wide ([fine | middle], decoder.py:182-187); its middle half needs five
+// more accumulators than a CTA's TMEM holds, so a fourth role (FINE_CM) repeats the fine decoder's hidden chain (Wh only)
+// and accumulates  Q_i[:, 32:64].
+#include "ens_tc.cuh"
+
+namespace ens {
+
+enum { ROLE_MIDDLE = 0, ROLE_FINE = 1, ROLE_COLOR = 2, ROLE_FINE_CM = 3 };
+
+// raw (folded-network) weight-gradient sums of one role, floats
+constexpr int RAW_ACC = 8 * 2048;                 // 8 accumulators [64 rows][32 units]
+constexpr int RAW_BHAT = RAW_ACC;                 // [5][32]   sum g_u_i
+constexpr int RAW_DWOR = RAW_BHAT + 160;          // [4][32]   sum g_out[o] r_4[k]
+constexpr int RAW_QO = RAW_DWOR + 128;            // [4][32]   sum g_out[o] c[ch]
+constexpr int RAW_DBO = RAW_QO + 128;             // [4]
+constexpr int RAW_DB = RAW_DBO + 4;               // [3][96]   sum p[r] g_q[k]
+constexpr int RAW_FLOATS = ((RAW_DB + 288 + 63) / 64) * 64;
+
+struct BwdTcArgs {
+  DevScene sc;
+  const double *pts;        // [P][3]
+  const float4 *gout;       // [P]  (g_r, g_g, g_b, g_occ)
+  int64_t P, n_tiles;       // n_tiles = ceil(P / 128)
+  const float *save_r;      // [3 decoders][n_tiles][5][128][32]   (decoder gradients wanted)
+  const uint32_t *save_m;   // [3 decoders][m_stride]: per 32-point tile [5][32] mask words (pose only)
+  int64_t m_stride;
+  float *ggrid[4];
+  float *raw_acc;           // [4 roles][RAW_FLOATS]
+  float *gp;                // [3 planes][P][3], or null
+  int ctas[4];              // persistent CTAs per role
+};
+
+// TMEM columns
+constexpr int TB_XH = 0, TB_XL = 32, TB_DH = 64, TB_DC = 96, TB_DE = 128, TB_ACC = 224;
+
+__device__ __forceinline__ void cta_sync128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// column sums over the warp: lane k gets sum_lanes v[k]  (reduce-scatter: 16 + 8 + 4 + 2 + 1 shuffles)
+__device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  float a16[16], a8[8], a4[4], a2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float mine = h16 ? v[16 + j] : v[j], send = h16 ? v[j] : v[16 + j];
+    a16[j] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mine = h8 ? a16[8 + j] : a16[j], send = h8 ? a16[j] : a16[8 + j];
+    a8[j] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mine = h4 ? a8[4 + j] : a8[j], send = h4 ? a8[j] : a8[4 + j];
+    a4[j] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float mine = h2 ? a4[2 + j] : a4[j], send = h2 ? a4[j] : a4[2 + j];
+    a2[j] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const float mine = h1 ? a2[1] : a2[0], send = h1 ? a2[0] : a2[1];
+  return mine + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// stage one point's 32 values as row `pt` of an MN-major [128][32] block pair (value, TF32 remainder)
+__device__ __forceinline__ void stage_row(float *__restrict__ hi, float *__restrict__ lo, int pt, const float (&v)[32]) {
+  float *rh = hi + pt * 32, *rl = lo + pt * 32;
+  const int sw = pt & 3;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 h = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    float4 l;
+    l.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xffffe000u);
+    l.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xffffe000u);
+    l.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xffffe000u);
+    l.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xffffe000u);
+    const int off = (((q >> 1) ^ sw) << 3) | ((q & 1) << 2);        // 32-byte chunk (q / 2) ^ (pt % 4), half q % 2
+    *reinterpret_cast<float4 *>(rh + off) = h;
+    *reinterpret_cast<float4 *>(rl + off) = l;
+  }
+}
+
+// one weight-gradient pass: acc[128 x 32] += [A blocks 0..3]^T-by-points x g  (B = value, then remainder)
+__device__ __forceinline__ void issue_wgrad(uint32_t acc, uint32_t sA, uint32_t sB) {
+  constexpr uint32_t IDESC = tc_idesc_mn(128, 32);
+  const uint64_t da = umma_desc_mn(sA, 16384u), dbh = umma_desc_mn(sB, 16384u), dbl = umma_desc_mn(sB + 16384u, 16384u);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbl + (uint64_t)(64 * ks), IDESC, 1u);
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
+}
+
+template <int ROLE, bool WG>
+__device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw) {
+  constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
+  constexpr int CD = (LEVEL == ENS_LEVEL_FINE) ? 64 : 32;
+  constexpr int NO = (ROLE == ROLE_COLOR) ? 3 : 1;              // outputs that carry gradient (decoder.py:341 drops colour's 4th)
+  constexpr int DEC = (ROLE == ROLE_MIDDLE) ? 0 : (ROLE == ROLE_COLOR ? 2 : 1);
+  constexpr bool TAIL = ROLE != ROLE_FINE_CM;                    // scatter / embedding / d L / d p
+  constexpr int CLEVEL = (ROLE == ROLE_FINE_CM) ? ENS_LEVEL_MIDDLE : LEVEL;     // level whose features fill slot B
+  using PB = MlpPackTCB;
+  static_assert(!(ROLE == ROLE_FINE_CM) || WG, "the FINE_CM role only exists for decoder gradients");
+
+  // ---- shared memory: [M-side 4 blocks | N-side 2 blocks] (WG) or one staging block, then the weight blob ----
+  float *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) / 4;    // swizzle atoms need SHARED-space alignment
+  float *sMB = base;                                   // hiA, hiB, loA, loB   (hiA doubles as the warps' 32x32 staging tiles)
+  float *sNB = base + (WG ? 16384 : 4096);             // g_hi, g_lo
+  float *sw = sNB + (WG ? 8192 : 0);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float4 sP[128];                           // p.float() of the tile's points (dB reduction)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float *stile = sMB + warp * 1024;
+  constexpr uint32_t TCOLS = WG ? 512u : 256u;
+
+  {
+    const float *gw = a.sc.w[LEVEL] + off_tcb<CD>();
+    const uint32_t s0 = smem_u32(sw);
+    for (int i = tid; i < PB::total() / 4; i += 128)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(TCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb0 = tmem_base_s;
+  const uint32_t tb = tb0 + ((uint32_t)(32 * warp) << 16);
+  const uint32_t swb = smem_u32(sw), sMBa = smem_u32(sMB), sNBa = smem_u32(sNB);
+  uint32_t parity = 0;
+
+  if (WG) {      // the weight-gradient accumulators start at zero and only ever accumulate
+    uint32_t zz[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) zz[k] = 0u;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                   "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+                   "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                   :: "r"(tb + TB_ACC + 32 * c), "r"(zz[0]), "r"(zz[1]), "r"(zz[2]), "r"(zz[3]), "r"(zz[4]), "r"(zz[5]), "r"(zz[6]), "r"(zz[7]),
+                     "r"(zz[8]), "r"(zz[9]), "r"(zz[10]), "r"(zz[11]), "r"(zz[12]), "r"(zz[13]), "r"(zz[14]), "r"(zz[15]),
+                     "r"(zz[16]), "r"(zz[17]), "r"(zz[18]), "r"(zz[19]), "r"(zz[20]), "r"(zz[21]), "r"(zz[22]), "r"(zz[23]),
+                     "r"(zz[24]), "r"(zz[25]), "r"(zz[26]), "r"(zz[27]), "r"(zz[28]), "r"(zz[29]), "r"(zz[30]), "r"(zz[31])
+                   : "memory");
+    }
+    tmem_st_done();
+    tc_fence_before();
+    cta_sync128();
+    tc_fence_after();
+  }
+
+  // per-lane sums that live in registers across the CTA's tiles (lane k = column k; one partial per warp)
+  float bhat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float dwor[NO], qo[NO], dbo[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) dwor[o] = qo[o] = dbo[o] = 0.f;
+  float dBacc[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+
+  const bool want_rays = TAIL && a.gp != nullptr;
+  const int nctas = a.ctas[ROLE];
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+    const int64_t pt = tile * 128 + tid;
+    const bool valid = pt < a.P;
+    double p[3] = {0.0, 0.0, 0.0};
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const double *pp = a.pts + pt * 3;
+      p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
+      g4 = a.gout[pt];
+    }
+    float pn[3], p32[3];
+    normalize64(p, a.sc.lo, a.sc.hi, pn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p32[k] = __double2float_rn(p[k]);
+    float go[NO];
+    if (ROLE == ROLE_COLOR) { go[0] = g4.x; if (NO > 1) { go[1 % NO] = g4.y; go[2 % NO] = g4.z; } }
+    else go[0] = g4.w;
+    const Vox vox = make_vox(pn, a.sc.dims[LEVEL]);
+
+    // ---- features of the point (operand of Q_i = sum g_u_i^T c) -> slot B, value + remainder ----
+    float c[32];
+    if (WG) {
+      const Vox vc = (CLEVEL == LEVEL) ? vox : make_vox(pn, a.sc.dims[CLEVEL]);
+      __syncwarp();
+      gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, stile, 0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 x = *reinterpret_cast<const float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3)));
+        c[4 * q] = x.x; c[4 * q + 1] = x.y; c[4 * q + 2] = x.z; c[4 * q + 3] = x.w;
+      }
+      __syncwarp();
+      stage_row(sMB + 4096, sMB + 3 * 4096, tid, c);
+    }
+    if (WG && TAIL) sP[tid] = make_float4(p32[0], p32[1], p32[2], 0.f);
+
+    // ---- g_h4 = Wo^T g_out ----
+    float g[32];
+    {
+      const float *Wo = sw + PB::off_Wo();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) s = fmaf(Wo[o * 32 + k], go[o], s);
+        g[k] = s;
+      }
+    }
+    const float *rbase = WG ? a.save_r + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + tid * 32 : nullptr;
+    float rcur[32];
+    if (WG) {
+      const float4 *src = reinterpret_cast<const float4 *>(rbase + 4 * 4096);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const float4 x = __ldg(src + q); rcur[4 * q] = x.x; rcur[4 * q + 1] = x.y; rcur[4 * q + 2] = x.z; rcur[4 * q + 3] = x.w; }
+      // output layer: sum g_out[o] r_4[k], sum g_out[o] c[ch], sum g_out[o]
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        float t[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = go[o] * rcur[k];
+        dwor[o] += warp_colsum32(t);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = go[o] * c[k];
+        qo[o] += warp_colsum32(t);
+        float sg = go[o];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, off);
+        dbo[o] += sg;
+      }
+    }
+
+    // ---- blocks 4..0 ----
+#pragma unroll 1
+    for (int i = 4; i >= 0; --i) {
+      float gu[32];
+      if (WG) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) gu[k] = (rcur[k] > 0.f) ? g[k] : 0.f;
+      } else {
+        const uint32_t mw = valid ? a.save_m[(int64_t)DEC * a.m_stride + (pt >> 5) * 160 + i * 32 + (pt & 31)] : 0u;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) gu[k] = ((mw >> k) & 1u) ? g[k] : 0.f;
+      }
+      if (WG) {
+        const float bs = warp_colsum32(gu);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (k == i) bhat[k] += bs;
+        stage_row(sNB, sNB + 4096, tid, gu);
+        if (i >= 1) {                                   // slot A: r_{i-1}, which is also the next block's relu mask
+          const float4 *src = reinterpret_cast<const float4 *>(rbase + (i - 1) * 4096);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const float4 x = __ldg(src + q); rcur[4 * q] = x.x; rcur[4 * q + 1] = x.y; rcur[4 * q + 2] = x.z; rcur[4 * q + 3] = x.w; }
+          stage_row(sMB, sMB + 2 * 4096, tid, rcur);
+        } else if (TAIL) {                              // block 0: slot A = Fourier chunk 0
+          float e[32];
+          const float *B = sw + PB::off_B();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) e[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + k], fmaf(p32[1], B[EMBP + k], p32[0] * B[k])));
+          stage_row(sMB, sMB + 2 * 4096, tid, e);
+        }
+      }
+      const bool need_a = (i >= 1) || TAIL;             // block 0's g_u only feeds the embedding gradient
+      if (need_a) tmem_st32_split(tb + TB_XH, tb + TB_XL, gu);
+      tmem_st_done();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      cta_sync128();
+      if (warp == 0) {
+        tc_fence_after();
+        if (i >= 1) {
+          issue_gemm<32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_WhT(1) + (i - 1) * 1024, PB::TOT(), 0u);
+          if (TAIL) issue_gemm<32, 32>(tb0 + TB_DC, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_MT(0) + (i - 1) * 1024, PB::TOT(), i == 4 ? 0u : 1u);
+        }
+        if (TAIL && (i == 3 || i == 0))
+          issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, i == 3 ? PB::off_W3eT() : PB::off_W0T(), PB::TOT(), i == 3 ? 0u : 1u);
+        if (WG) {
+          // accumulators: 0 L4 [r3|c]  1 L3 [r2|c]  2 L3 [e0|e1]  3 L3 [e2|c]  4 L2 [r1|c]  5 L1 [r0|c]  6 L0 [e0|c]  7 L0 [e1|e2]
+          // (FINE_CM: 4 - i, rows 32..63 = c_middle)
+          const int acc = (ROLE == ROLE_FINE_CM) ? (4 - i) : (i == 4 ? 0 : (i == 3 ? 1 : (i == 2 ? 4 : (i == 1 ? 5 : 6))));
+          issue_wgrad(tb0 + TB_ACC + 32 * acc, sMBa, sNBa);
+        }
+        umma_commit(&bar);
+        __syncwarp();
+      }
+      mbar_wait(&bar, parity); parity ^= 1;
+      tc_fence_after();
+      if (i >= 1) tmem_ld32(tb + TB_DH, g);
+      // ---- the Fourier-feature operands of blocks 3 and 0:  E_i = sum g_u_i^T e ----
+      if (WG && TAIL && (i == 3 || i == 0)) {
+        const float *B = sw + PB::off_B();
+        float e[32];
+        // pass 1: i == 3: [e0 | e1] (slot B loses c);  i == 0: [e1 | e2] (c is dead after block 0)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int jc = (i == 3) ? h : 1 + h;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            e[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * jc + k], fmaf(p32[1], B[EMBP + 32 * jc + k], p32[0] * B[32 * jc + k])));
+          stage_row(sMB + h * 4096, sMB + (2 + h) * 4096, tid, e);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        cta_sync128();
+        if (warp == 0) {
+          tc_fence_after();
+          issue_wgrad(tb0 + TB_ACC + 32 * (i == 3 ? 2 : 7), sMBa, sNBa);
+          umma_commit(&bar);
+          __syncwarp();
+        }
+        mbar_wait(&bar, parity); parity ^= 1;
+        tc_fence_after();
+        if (i == 3) {       // pass 2: [e2 | c] -- slot B gets the features back for blocks 2, 1, 0
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            e[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 64 + k], fmaf(p32[1], B[EMBP + 64 + k], p32[0] * B[64 + k])));
+          stage_row(sMB, sMB + 2 * 4096, tid, e);
+          stage_row(sMB + 4096, sMB + 3 * 4096, tid, c);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          tc_fence_before();
+          cta_sync128();
+          if (warp == 0) {
+            tc_fence_after();
+            issue_wgrad(tb0 + TB_ACC + 32 * 3, sMBa, sNBa);
+            umma_commit(&bar);
+            __syncwarp();
+          }
+          mbar_wait(&bar, parity); parity ^= 1;
+          tc_fence_after();
+        }
+      }
+    }
+
+    // ---- tail: feature gradient -> grid scatter + coordinate gradient; embedding gradient ----
+    if (TAIL) {
+      double gp[3] = {0.0, 0.0, 0.0};
+      float *ggrid = a.ggrid[LEVEL];
+      if (ggrid != nullptr || want_rays) {
+        float gc[32];
+        tmem_ld32(tb + TB_DC, gc);
+        const float *MoF = sw + PB::off_MoF();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float s = gc[k];
+#pragma unroll
+          for (int o = 0; o < NO; ++o) s = fmaf(MoF[o * 32 + k], go[o], s);
+          gc[k] = s;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
+        __syncwarp();
+        float gpn[3];
+        gather_bwd_warp<32>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], vox, valid, stile, want_rays, gpn);
+        if (want_rays) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) gp[k] += __ddiv_rn((double)gpn[k] * 2.0, __dsub_rn(a.sc.hi[k], a.sc.lo[k]));
+        }
+        __syncwarp();
+      }
+      if (WG || want_rays) {
+        const float *B = sw + PB::off_B();
+        float gpe[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int jc = 0; jc < 3; ++jc) {
+          float ge[32];
+          tmem_ld32(tb + TB_DE + 32 * jc, ge);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float bx = B[32 * jc + k], by = B[EMBP + 32 * jc + k], bz = B[2 * EMBP + 32 * jc + k];
+            float sq, cq;
+            fast_sincos(fmaf(p32[2], bz, fmaf(p32[1], by, p32[0] * bx)), sq, cq);
+            const float gq = ge[k] * cq;
+            ge[k] = gq;
+            gpe[0] = fmaf(bx, gq, gpe[0]); gpe[1] = fmaf(by, gq, gpe[1]); gpe[2] = fmaf(bz, gq, gpe[2]);
+          }
+          if (WG) {
+            // dB[r][32 jc + k] = sum_pt p[pt][r] g_q[pt][k]: transpose through the warp's tile, lane k walks its column
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float v = stile[r * 32 + (lane ^ ((r & 3) << 3))];
+              const float4 pr = sP[32 * warp + r];
+              s0 = fmaf(pr.x, v, s0); s1 = fmaf(pr.y, v, s1); s2 = fmaf(pr.z, v, s2);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q == jc) { dBacc[q][0] += s0; dBacc[q][1] += s1; dBacc[q][2] += s2; }
+            __syncwarp();
+          }
+        }
+        if (want_rays) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) gp[k] += (double)gpe[k];
+        }
+      }
+      if (want_rays && valid) {
+        float *dst = a.gp + ((int64_t)DEC * a.P + pt) * 3;
+        dst[0] = (float)gp[0]; dst[1] = (float)gp[1]; dst[2] = (float)gp[2];
+      }
+    }
+    // the next tile's staging / tcgen05.st must not overtake this tile's TMEM loads and shared-tile reads
+    tc_fence_before();
+    cta_sync128();
+    tc_fence_after();
+  }
+
+  // ---- flush the CTA's sums ----
+  if (WG) {
+    float *raw = a.raw_acc + (int64_t)ROLE * RAW_FLOATS;
+    constexpr int NACC = (ROLE == ROLE_FINE_CM) ? 5 : 8;
+#pragma unroll 1
+    for (int acc = 0; acc < NACC; ++acc) {
+      float v[32];
+      tmem_ld32(tb + TB_ACC + 32 * acc, v);
+      float *dst = raw + acc * 2048 + (tid & 63) * 32;              // lanes 64..127 hold the remainder products of rows 0..63
+#pragma unroll
+      for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      atomicAdd(raw + RAW_DWOR + o * 32 + lane, dwor[o]);
+      atomicAdd(raw + RAW_QO + o * 32 + lane, qo[o]);
+      if (lane == 0) atomicAdd(raw + RAW_DBO + o, dbo[o]);
+    }
+    if (TAIL) {
+#pragma unroll
+      for (int jc = 0; jc < 3; ++jc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) atomicAdd(raw + RAW_DB + r * 96 + 32 * jc + lane, dBacc[jc][r]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(TCOLS) : "memory");
+}
+
+template <int STAGE, bool WG>
+__global__ void __launch_bounds__(128, 1) bwd_tc_kernel(BwdTcArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  const int role = blockIdx.y;
+  if ((int)blockIdx.x >= a.ctas[role]) return;
+  if (role == ROLE_MIDDLE) bwd_tc_body<ROLE_MIDDLE, WG>(a, smem);
+  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE, WG>(a, smem); }
+  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_body<ROLE_COLOR, WG>(a, smem); }
+  else { if constexpr (WG && STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE_CM, true>(a, smem); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw2outputs_nerf_color backward (common.py:256-297), one warp per ray: the lanes fetch the samples and
+// evaluate the sigmoids, lane 0 runs the sequential products / sums in the order of the fused kernels, the lanes write
+// d L / d (decoder outputs) of their samples.  Out-of-bound samples (Renderer.py:58 overwrote their occupancy) get none.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) composite_bwd_kernel(DevScene sc, const float4 *__restrict__ raw, const double *__restrict__ z,
+                                                            const double *__restrict__ pts, int64_t R, int S,
+                                                            const double *__restrict__ g_depth, const double *__restrict__ g_var,
+                                                            const float *__restrict__ g_color, float4 *__restrict__ gout) {
+  __shared__ float4 s_raw[4][ENS_MAX_SAMPLES];
+  __shared__ double s_z[4][ENS_MAX_SAMPLES], s_gw[4][ENS_MAX_SAMPLES];
+  __shared__ float s_a[4][ENS_MAX_SAMPLES], s_T[4][ENS_MAX_SAMPLES], s_w[4][ENS_MAX_SAMPLES], s_suf[4][ENS_MAX_SAMPLES];
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + wi;
+  if (ray >= R) return;
+  for (int k = lane; k < S; k += 32) {
+    const int64_t pi = ray * S + k;
+    const float4 r4 = raw[pi];
+    s_raw[wi][k] = r4;
+    s_z[wi][k] = z[pi];
+    s_a[wi][k] = 1.f / (1.f + expf(-(10.f * r4.w)));
+  }
+  __syncwarp();
+  float gcl[3] = {0.f, 0.f, 0.f};
+  if (g_color) { gcl[0] = g_color[ray * 3]; gcl[1] = g_color[ray * 3 + 1]; gcl[2] = g_color[ray * 3 + 2]; }
+  if (lane == 0) {
+    float T = 1.f;
+    for (int k = 0; k < S; ++k) {
+      s_T[wi][k] = T;
+      s_w[wi][k] = __fmul_rn(s_a[wi][k], T);
+      T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.f, s_a[wi][k]), 1e-10f));
+    }
+    double dep = 0.0;
+    for (int k = 0; k < S; ++k) dep += (double)s_w[wi][k] * s_z[wi][k];
+    double wdz = 0.0;
+    for (int k = 0; k < S; ++k) wdz += (double)s_w[wi][k] * (s_z[wi][k] - dep);
+    const double gd = g_depth ? g_depth[ray] : 0.0;
+    const double gv = g_var ? g_var[ray] : 0.0;
+    const double gdt = gd + gv * (-2.0 * wdz);
+    for (int k = 0; k < S; ++k) {
+      const float4 rk = s_raw[wi][k];
+      const double zk = s_z[wi][k], dz = zk - dep;
+      s_gw[wi][k] = (double)rk.x * gcl[0] + (double)rk.y * gcl[1] + (double)rk.z * gcl[2] + gdt * zk + gv * dz * dz;
+    }
+    float accs = 0.f;
+    for (int k = S - 1; k >= 0; --k) {
+      s_suf[wi][k] = accs;
+      accs += s_w[wi][k] * (float)s_gw[wi][k];
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < S; k += 32) {
+    const int64_t pi = ray * S + k;
+    bool inside = true;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const double pk = pts[pi * 3 + q]; inside &= (pk < sc.hi[q]) && (pk > sc.lo[q]); }
+    const float alpha = s_a[wi][k];
+    const float gw = (float)s_gw[wi][k];
+    const float om = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    const float g_alpha = s_T[wi][k] * gw - s_suf[wi][k] / om;
+    const float wv = s_w[wi][k];
+    gout[pi] = make_float4(wv * gcl[0], wv * gcl[1], wv * gcl[2], inside ? 10.f * alpha * (1.f - alpha) * g_alpha : 0.f);
+  }
+}
+
+// g_rays_o = sum_s g_p, g_rays_d = sum_s z_s g_p over the role planes (float64 sums, as the fused kernels)
+__global__ void __launch_bounds__(128) rays_reduce_kernel(const float *__restrict__ gp, int n_planes, const double *__restrict__ z,
+                                                          int64_t R, int S, float *__restrict__ g_rays_o, float *__restrict__ g_rays_d) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ray = t / 3;
+  const int s = (int)(t % 3);
+  if (ray >= R) return;
+  const int64_t P = R * (int64_t)S;
+  double so = 0.0, sd = 0.0;
+  for (int k = 0; k < S; ++k) {
+    const int64_t pi = ray * S + k;
+    double gk = 0.0;
+    for (int q = 0; q < n_planes; ++q) gk += (double)gp[((int64_t)q * P + pi) * 3 + s];
+    so += gk;
+    sd += gk * z[pi];
+  }
+  if (g_rays_o) g_rays_o[ray * 3 + s] = (float)so;
+  if (g_rays_d) g_rays_d[ray * 3 + s] = (float)sd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// folded sums -> the reference's parameter gradients (see the header of this file).  One CTA per decoder.
+// blob: the decoder's packed weights (fma section MlpPack<CD>: W_iT [K_i][32], b_i, Wc_iT [CD][32], bc_i, WoT [32][4], bo).
+// ---------------------------------------------------------------------------------------------
+// NO = output rows that carry gradient, NOF = rows of output_linear (the colour decoder's 4th row gets none, decoder.py:341)
+template <int CD, int NO, int NOF>
+__device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const float *__restrict__ raw_cm,
+                                            const float *__restrict__ blob, float *__restrict__ gdec) {
+  using PK = MlpPack<CD>;
+  using GO = MlpGrad<CD, NOF>;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  auto accS = [](int i) { return i == 4 ? 0 : (i == 3 ? 1 : (i == 2 ? 4 : 5)); };                  // i = 1..4
+  auto S = [&](int i, int n, int k) { return raw[accS(i) * 2048 + k * 32 + n]; };
+  auto Q = [&](int i, int n, int ch) {                                                             // i = 0..4
+    if (ch >= 32) return raw_cm[(4 - i) * 2048 + ch * 32 + n];                                     // FINE_CM rows 32..63
+    const int acc = (i == 0) ? 6 : accS(i);
+    return raw[acc * 2048 + (32 + ch) * 32 + n];
+  };
+  auto bhat = [&](int i, int n) { return raw[RAW_BHAT + i * 32 + n]; };
+  auto Qo = [&](int o, int ch) { return ch >= 32 ? raw_cm[RAW_QO + o * 32 + ch - 32] : raw[RAW_QO + o * 32 + ch]; };
+  auto Wh = [&](int i, int n, int k) { return blob[PK::off_W(i) + ((i == 3 ? EMB : 0) + k) * 32 + n]; };   // hidden part of W_i, i = 1..4
+  auto Wc = [&](int i, int k, int ch) { return blob[PK::off_Wc(i) + ch * 32 + k]; };                        // fc_c[i].weight[k][ch]
+  auto bc = [&](int i, int k) { return blob[PK::off_bc(i) + k]; };
+  auto Wo = [&](int o, int k) { return blob[PK::off_Wo() + k * 4 + o]; };
+
+  // fc_c.i.weight [32][CD], fc_c.i.bias [32]
+  for (int idx = tid; idx < 5 * 32 * CD; idx += nt) {
+    const int i = idx / (32 * CD), k = (idx / CD) % 32, ch = idx % CD;
+    double s = 0.0;
+    if (i < 4) { for (int n = 0; n < 32; ++n) s += (double)Wh(i + 1, n, k) * (double)Q(i + 1, n, ch); }
+    else { for (int o = 0; o < NO; ++o) s += (double)Wo(o, k) * (double)Qo(o, ch); }
+    gdec[GO::off_Wc(i) + k * CD + ch] += (float)s;
+  }
+  for (int idx = tid; idx < 5 * 32; idx += nt) {
+    const int i = idx / 32, k = idx % 32;
+    double s = 0.0;
+    if (i < 4) { for (int n = 0; n < 32; ++n) s += (double)Wh(i + 1, n, k) * (double)bhat(i + 1, n); }
+    else { for (int o = 0; o < NO; ++o) s += (double)Wo(o, k) * (double)raw[RAW_DBO + o]; }
+    gdec[GO::off_bc(i) + k] += (float)s;
+    gdec[GO::off_b(i) + k] += bhat(i, k);                                                   // pts_linears.i.bias
+  }
+  // embedder._B [3][93]
+  for (int idx = tid; idx < 3 * EMB; idx += nt) gdec[GO::off_B() + idx] += raw[RAW_DB + (idx / EMB) * 96 + idx % EMB];
+  // pts_linears.0.weight [32][93] and the embedding half of pts_linears.3.weight [32][125]
+  for (int idx = tid; idx < 32 * EMB; idx += nt) {
+    const int n = idx / EMB, k = idx % EMB;
+    const float e0 = (k < 32) ? raw[6 * 2048 + k * 32 + n] : raw[7 * 2048 + (k - 32) * 32 + n];
+    const float e3 = (k < 64) ? raw[2 * 2048 + k * 32 + n] : raw[3 * 2048 + (k - 64) * 32 + n];
+    gdec[GO::off_W(0) + n * EMB + k] += e0;
+    gdec[GO::off_W(3) + n * 125 + k] += e3;
+  }
+  // hidden parts of pts_linears.1..4.weight:  S_i + Q_i Wc_{i-1}^T + b^_i bc_{i-1}^T
+  for (int idx = tid; idx < 4 * 1024; idx += nt) {
+    const int i = 1 + idx / 1024, n = (idx / 32) % 32, k = idx % 32;
+    double s = (double)S(i, n, k) + (double)bhat(i, n) * (double)bc(i - 1, k);
+    for (int ch = 0; ch < CD; ++ch) s += (double)Q(i, n, ch) * (double)Wc(i - 1, k, ch);
+    const int K = (i == 3) ? 125 : 32;
+    gdec[GO::off_W(i) + n * K + (i == 3 ? EMB : 0) + k] += (float)s;
+  }
+  // output_linear.weight [NO_full][32], bias  (NO rows carry gradient; the colour decoder's 4th row gets none)
+  for (int idx = tid; idx < NO * 32; idx += nt) {
+    const int o = idx / 32, k = idx % 32;
+    double s = (double)raw[RAW_DWOR + o * 32 + k] + (double)raw[RAW_DBO + o] * (double)bc(4, k);
+    for (int ch = 0; ch < CD; ++ch) s += (double)Qo(o, ch) * (double)Wc(4, k, ch);
+    gdec[GO::off_Wo() + o * 32 + k] += (float)s;
+  }
+  for (int o = tid; o < NO; o += nt) gdec[GO::off_bo() + o] += raw[RAW_DBO + o];
+}
+
+struct UnfoldArgs {
+  const float *raw;        // [4 roles][RAW_FLOATS]
+  const float *w[4];       // packed blobs
+  float *gdec[4];
+};
+
+__global__ void __launch_bounds__(256) unfold_kernel(UnfoldArgs a, int stage) {
+  const int d = blockIdx.x;
+  if (d == 0) unfold_body<32, 1, 1>(a.raw + ROLE_MIDDLE * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_MIDDLE], a.gdec[ENS_LEVEL_MIDDLE]);
+  else if (d == 1) {
+    if (stage >= ENS_STAGE_FINE)
+      unfold_body<64, 1, 1>(a.raw + ROLE_FINE * RAW_FLOATS, a.raw + ROLE_FINE_CM * RAW_FLOATS, a.w[ENS_LEVEL_FINE], a.gdec[ENS_LEVEL_FINE]);
+  } else if (stage == ENS_STAGE_COLOR) {
+    unfold_body<32, 3, 4>(a.raw + ROLE_COLOR * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_COLOR], a.gdec[ENS_LEVEL_COLOR]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT_MMA) place_bwd_kernel(DevScene sc, RayArgs ra, double *__restrict__ z_out,
+                                                           double *__restrict__ pts) {
+  __shared__ double zc[NT_MMA], zs[NT_MMA];
+  const int S = ra.S;
+  const int rl = threadIdx.x / S, s = threadIdx.x % S;
+  const int64_t ray = (int64_t)blockIdx.x * ra.rpc + rl;
+  const bool valid = (rl < ra.rpc) && (ray < ra.R);
+  float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = ra.rays_o[ray * 3 + k]; d[k] = ra.rays_d[ray * 3 + k]; }
+  }
+  const double z = place_sample(ra, sc, valid, ray, rl, s, o, d, zc, zs);
+  if (valid) {
+    const int64_t pi = ray * S + s;
+    z_out[pi] = z;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pts[pi * 3 + k] = __dadd_rn((double)o[k], __dmul_rn((double)d[k], z));   // Renderer.py:173-174
+  }
+}
+
+// workspace: points [P][3] f64 | z [P] f64 | g_out [P][4] | g_p planes [3][P][3] | raw sums [4][RAW_FLOATS]
+int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage) {
+  if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
+  const int64_t P = n_rays * (int64_t)S;
+  return P * (24 + 8 + 16 + 36) + 4 * (int64_t)RAW_FLOATS * 4 + 256;
+}
+
+template <int STAGE, bool WG>
+static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStream_t s) {
+  const size_t smem = (size_t)((WG ? 16384 + 8192 : 4096) + MlpPackTCB::total()) * 4 + 1024;
+  if (cudaFuncSetAttribute(bwd_tc_kernel<STAGE, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  bwd_tc_kernel<STAGE, WG><<<dim3((unsigned)max_ctas, (unsigned)nroles), 128, smem, s>>>(a);
+  ENS_CHECK_CUDA();
+  return ENS_OK;
+}
+
+int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t workspace_bytes, cudaStream_t s) {
+  if (stage == ENS_STAGE_COARSE) return ENS_EUNSUPPORTED;
+  const int64_t R = b.ra.R;
+  const int S = b.ra.S;
+  const int64_t P = R * (int64_t)S;
+  if (!workspace || workspace_bytes < tc_bwd_workspace_bytes(R, S, stage)) return ENS_ESHAPE;
+  if (wg ? (b.save_r == nullptr) : (b.save_masks == nullptr)) return ENS_EINVAL;
+  char *base = reinterpret_cast<char *>(workspace);
+  double *pts = reinterpret_cast<double *>(base);
+  double *z = reinterpret_cast<double *>(base + P * 24);
+  float4 *gout = reinterpret_cast<float4 *>(base + P * 32);
+  float *gp = reinterpret_cast<float *>(base + P * 48);
+  float *raw = reinterpret_cast<float *>(base + ((P * 84 + 255) / 256) * 256);
+  const bool want_rays = b.g_rays_o != nullptr || b.g_rays_d != nullptr;
+
+  b.ra.rpc = NT_MMA / S;
+  place_bwd_kernel<<<(unsigned)((R + b.ra.rpc - 1) / b.ra.rpc), NT_MMA, 0, s>>>(b.sc, b.ra, z, pts);
+  ENS_CHECK_CUDA();
+  composite_bwd_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(b.sc, reinterpret_cast<const float4 *>(b.raw), z, pts, R, S,
+                                                              b.g_depth, b.g_var, b.g_color, gout);
+  ENS_CHECK_CUDA();
+  if (wg && cudaMemsetAsync(raw, 0, 4 * (size_t)RAW_FLOATS * 4, s) != cudaSuccess) return ENS_ECUDA;
+
+  BwdTcArgs a;
+  a.sc = b.sc; a.pts = pts; a.gout = gout; a.P = P; a.n_tiles = (P + 127) / 128;
+  a.save_r = b.save_r; a.save_m = b.save_masks; a.m_stride = b.n_tiles * 160;
+  for (int l = 0; l < 4; ++l) a.ggrid[l] = b.ggrid[l];
+  a.raw_acc = raw; a.gp = want_rays ? gp : nullptr;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ENS_ECUDA;
+  // persistent CTAs per role, in proportion to the work of a tile (the FINE_CM role runs the hidden chain only)
+  const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
+  const int nroles = (wg && ndec > 1) ? 4 : ndec;
+  const double cost[4] = {1.0, 1.0, 1.0, 0.45};
+  double tot = 0.0;
+  for (int r = 0; r < 4; ++r) { a.ctas[r] = 0; if (r < ndec || (r == 3 && nroles == 4)) tot += cost[r]; }
+  int max_ctas = 0;
+  for (int r = 0; r < 4; ++r) {
+    if (!(r < ndec || (r == 3 && nroles == 4))) continue;
+    int64_t n = (int64_t)(sms * cost[r] / tot);
+    if (n < 1) n = 1;
+    if (n > a.n_tiles) n = a.n_tiles;
+    a.ctas[r] = (int)n;
+    if ((int)n > max_ctas) max_ctas = (int)n;
+  }
+  int rc;
+#define ENS_TCB(ST) (wg ? launch_bwd_tc<ST, true>(a, nroles, max_ctas, s) : launch_bwd_tc<ST, false>(a, nroles, max_ctas, s))
+  if (stage == ENS_STAGE_MIDDLE) rc = ENS_TCB(ENS_STAGE_MIDDLE);
+  else if (stage == ENS_STAGE_FINE) rc = ENS_TCB(ENS_STAGE_FINE);
+  else rc = ENS_TCB(ENS_STAGE_COLOR);
+#undef ENS_TCB
+  if (rc != ENS_OK) return rc;
+  if (wg) {
+    UnfoldArgs u;
+    u.raw = raw;
+    for (int l = 0; l < 4; ++l) { u.w[l] = b.sc.w[l]; u.gdec[l] = b.gdec[l]; }
+    unfold_kernel<<<ndec, 256, 0, s>>>(u, stage);
+    ENS_CHECK_CUDA();
+  }
+  if (want_rays) {
+    rays_reduce_kernel<<<(unsigned)((R * 3 + 127) / 128), 128, 0, s>>>(gp, ndec, z, R, S, b.g_rays_o, b.g_rays_d);
+    ENS_CHECK_CUDA();
+  }
+  return ENS_OK;
+}
+
+}  // namespace ens

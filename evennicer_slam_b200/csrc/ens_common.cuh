@@ -181,17 +181,41 @@ struct MlpPackTC {
 };
 __host__ __device__ constexpr int canon_off(int n, int k, int K) { return (n / 8) * (K / 4) * 32 + (k / 4) * 32 + (n % 8) * 4 + (k % 4); }
 
+// ---------------------------------------------------------------------------------------------
+// Packed decoder blob, "tc backward" layout (tcgen05 data-gradient GEMMs  g_x = g_u W).  The TRANSPOSED matrices in the
+// same canonical K-major UMMA layout as MlpPackTC (K = 32 = the output units of the block), value then TF32 remainder
+// (TOT floats further).  The feature gradient uses the folded matrices of the forward:  g_c = sum_i M_i^T g_u_{i+1} + Mo^T g_out
+// (M_i = W_{i+1}[hidden] Wc_i), so the running gradient needs no un-masked g_h operand.  Only the first 32 feature
+// channels carry gradient (the fine decoder's middle half is no_grad, decoder.py:184-186), so the blob has one size.
+//   WhT_i [32 in][32 out], i = 1..4:   WhT_i[k][n] = Wh_i[n][k]
+//   MT_i  [32 ch][32 out], i = 0..3:   MT_i[c][n]  = M_i[n][c]
+//   W0T   [96][32], W3eT [96][32]:      W0T[k][n]  = pts_linears.0.weight[n][k]  (rows k >= 93 zero)
+//   then: B [3][96], Wo [4][32] (rows >= NO zero), MoF [4][32] = Mo[:, :32]
+// ---------------------------------------------------------------------------------------------
+struct MlpPackTCB {
+  __host__ __device__ static constexpr int off_WhT(int i) { return (i - 1) * 1024; }             // i = 1..4
+  __host__ __device__ static constexpr int off_MT(int i) { return 4096 + i * 1024; }             // i = 0..3
+  __host__ __device__ static constexpr int off_W0T() { return 8192; }
+  __host__ __device__ static constexpr int off_W3eT() { return 8192 + 32 * EMBP; }
+  __host__ __device__ static constexpr int TOT() { return 8192 + 2 * 32 * EMBP; }
+  __host__ __device__ static constexpr int off_B() { return 2 * TOT(); }
+  __host__ __device__ static constexpr int off_Wo() { return off_B() + 3 * EMBP; }
+  __host__ __device__ static constexpr int off_MoF() { return off_Wo() + 128; }
+  __host__ __device__ static constexpr int total() { return off_MoF() + 128; }
+};
+
 // A packed blob holds the fma layout, the mma forward layout and the mma backward layout (coarse: fma only).
 __host__ __device__ inline int packed_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarsePack::total();
-    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total() + MlpPackV2B::total() + MlpPackTC<64>::total();
-    default: return MlpPack<32>::total() + MlpPackV2<32>::total() + MlpPackV2B::total() + MlpPackTC<32>::total();
+    case ENS_LEVEL_FINE: return MlpPack<64>::total() + MlpPackV2<64>::total() + MlpPackV2B::total() + MlpPackTC<64>::total() + MlpPackTCB::total();
+    default: return MlpPack<32>::total() + MlpPackV2<32>::total() + MlpPackV2B::total() + MlpPackTC<32>::total() + MlpPackTCB::total();
   }
 }
 template <int CD> __host__ __device__ constexpr int off_v2() { return MlpPack<CD>::total(); }
 template <int CD> __host__ __device__ constexpr int off_v2b() { return MlpPack<CD>::total() + MlpPackV2<CD>::total(); }
 template <int CD> __host__ __device__ constexpr int off_tc() { return off_v2b<CD>() + MlpPackV2B::total(); }
+template <int CD> __host__ __device__ constexpr int off_tcb() { return off_tc<CD>() + MlpPackTC<CD>::total(); }
 __host__ __device__ inline int grad_floats(int level) {
   switch (level) {
     case ENS_LEVEL_COARSE: return CoarseGrad::total();

@@ -18,128 +18,9 @@
 // Two tiles are in flight per CTA (two groups of four warps with their own TMEM columns and barriers).
 // Completion of each MMA batch is tracked with tcgen05.commit -> mbarrier; thread sync around TMEM stores uses
 // tcgen05.wait::st + tcgen05.fence + bar.sync.  Verified first in isolation by tools/tc_probe.cu.
-#include "ens_mma.cuh"
+#include "ens_tc.cuh"
 
 namespace ens {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle: LBO = 128 B between the two K core matrices, SBO = (K/4)*128 B between 8-row groups
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)((128u >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;          // descriptor version 1 (Blackwell)
-  return d;
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128, K = 8, N from the instruction descriptor.  Executed by a
-// whole (converged) warp with identical operands; elect.sync picks the one lane that issues, so the surrounding code
-// stays warp-uniform (no per-instruction broadcast loops out of a divergent branch).
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-      :: "r"(d_tmem), "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "TC_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra TC_DONE_%=;\n\t"
-      "bra TC_WAIT_%=;\n\t"
-      "TC_DONE_%=:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-               "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// store 32 values as the A operand: the value itself (hi: the tensor core reads its top 19 bits) at `thi`, the TF32
-// remainder at `tlo`
-__device__ __forceinline__ void tmem_st32_split(uint32_t thi, uint32_t tlo, const float (&v)[32]) {
-  uint32_t h[32], l[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    h[i] = __float_as_uint(v[i]);
-    l[i] = __float_as_uint(v[i] - __uint_as_float(h[i] & 0xffffe000u));
-  }
-#define ENS_ST32(addr, r)                                                                                      \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                 \
-               "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "  \
-               "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"                                \
-               :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
-                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), \
-                 "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), \
-                 "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) \
-               : "memory")
-  ENS_ST32(thi, h);
-  ENS_ST32(tlo, l);
-#undef ENS_ST32
-}
-__device__ __forceinline__ void tmem_st_done() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// trilinear feature of one point into registers (same corner order / fma order as gather32 and gather_warp)
-__device__ __forceinline__ void gather_regs(const float *__restrict__ grid, const int dims[3], const float pn[3],
-                                            float (&f)[32]) {
-  const Vox v = make_vox(pn, dims);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    int64_t lin; float w;
-    corner(v, dims, c, lin, w);
-    const float4 *src = reinterpret_cast<const float4 *>(grid + lin);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 a = __ldg(src + q);
-      f[4 * q + 0] = fmaf(a.x, w, f[4 * q + 0]); f[4 * q + 1] = fmaf(a.y, w, f[4 * q + 1]);
-      f[4 * q + 2] = fmaf(a.z, w, f[4 * q + 2]); f[4 * q + 3] = fmaf(a.w, w, f[4 * q + 3]);
-    }
-  }
-}
-
-// instruction descriptor: f32 accumulate, TF32 x TF32, both K-major, N columns, M = 128
-__host__ __device__ constexpr uint32_t tc_idesc(int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-// issue  D (+)= A[128 x K] * W[32 x K]^T  in 3xTF32; A: hi at a_hi, lo at a_lo (TMEM columns), W: canonical smem
-// matrix at float offset w_off (value) and w_off + TOT (remainder).  first_acc: 0 = overwrite D with the first MMA.
-template <int K, int KMAT, int N = 32>
-__device__ __forceinline__ void issue_gemm(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t sw_base, int w_off, int tot,
-                                           uint32_t first_acc) {
-  // K columns of a [N][KMAT] canonical matrix starting at float offset w_off (a column offset of 4c inside the
-  // matrix is c*128 bytes and is folded into sw_base by the caller); SBO is that of the WHOLE matrix
-  const uint64_t dh = umma_desc(sw_base + (uint32_t)w_off * 4u, (KMAT / 4) * 128u);
-  const uint64_t dl = umma_desc(sw_base + (uint32_t)(w_off + tot) * 4u, (KMAT / 4) * 128u);
-  constexpr uint32_t IDESC = tc_idesc(N);
-  uint32_t acc = first_acc;
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) { umma_ts(d, a_lo + 8 * ks, dh + (uint64_t)(16 * ks), IDESC, acc); acc = 1; }
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dl + (uint64_t)(16 * ks), IDESC, 1);
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) umma_ts(d, a_hi + 8 * ks, dh + (uint64_t)(16 * ks), IDESC, 1);
-}
 
 struct TcArgs {
   DevScene sc;
@@ -151,6 +32,8 @@ struct TcArgs {
                           // (inside ? 1 : 0, 0, 0, occ), fine (0, 0, 0, occ), colour (r, g, b, 0) -- combined by composite_kernel
   uint32_t *msave;        // optional: this decoder's saved relu masks, one word per point and block --
                           // [n_tiles32][5][32], word (tile, i, j) = point 32 tile + j, bit k = unit k of block i active
+  float *rsave;           // optional: this decoder's relu outputs r_0..r_4 = relu(u_i), [n_tiles128][5][128][32] -- what the
+                          // tcgen05 backward (ens_bwd_tc.cu) needs for the weight gradients (saved kind 3)
 };
 
 // Two 128-point tiles are in flight per CTA: tile group 0 = warps 0-3, group 1 = warps 4-7; each owns 256 TMEM columns,
@@ -282,6 +165,11 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
         for (int k = 0; k < 32; ++k) mw |= (r[k] > 0.f ? 1u : 0u) << k;
         a.msave[(pt >> 5) * 160 + i * 32 + (pt & 31)] = mw;
       }
+      if (a.rsave != nullptr) {                   // saved for the backward with decoder gradients (every lane: padded tile)
+        float4 *dst = reinterpret_cast<float4 *>(a.rsave + ((tile * 5 + i) * 128 + gt) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = valid ? make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       if (i < 4) {
         tmem_st32_split(tb + TC_XH, tb + TC_XL, r);
         tmem_st_done();
@@ -358,6 +246,7 @@ struct TcMultiArgs {
   TcArgs base;
   float *out[3];
   uint32_t *msave[3];
+  float *rsave[3];
 };
 
 template <int STAGE>
@@ -367,6 +256,7 @@ __global__ void __launch_bounds__(256, 1) decode_tc_multi_kernel(TcMultiArgs m) 
   const int d = blockIdx.y;
   a.out4 = m.out[d];
   a.msave = m.msave[d];
+  a.rsave = m.rsave[d];
   a.separate = 1;
   if (d == 0) decode_tc_body<ENS_LEVEL_MIDDLE, 32, 1, true>(a, smem);
   else if (d == 1) decode_tc_body<ENS_LEVEL_FINE, 64, 1, true>(a, smem);
@@ -375,9 +265,9 @@ __global__ void __launch_bounds__(256, 1) decode_tc_multi_kernel(TcMultiArgs m) 
 
 template <int LEVEL, int CD, int NO>
 static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s,
-                            uint32_t *msave = nullptr) {
+                            uint32_t *msave = nullptr, float *rsave = nullptr) {
   TcArgs a;
-  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.separate = 0;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0;
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -398,14 +288,15 @@ static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_
 // NICE.forward / Renderer.eval_points for stages middle, fine, color: one launch per decoder of the stage.
 // msave / mstride: optional saved-mask buffer of the stage (decoder d = middle, fine, colour at msave + d * mstride words).
 int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
-                   float *out4, cudaStream_t s, uint32_t *msave, int64_t mstride) {
+                   float *out4, cudaStream_t s, uint32_t *msave, int64_t mstride, float *rsave, int64_t rstride) {
   if (stage == ENS_STAGE_COARSE) return ENS_EUNSUPPORTED;
-  int rc = launch_decode_tc<ENS_LEVEL_MIDDLE, 32, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_MIDDLE ? apply_mask : 0, out4, s, msave);
+  int rc = launch_decode_tc<ENS_LEVEL_MIDDLE, 32, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_MIDDLE ? apply_mask : 0, out4, s, msave, rsave);
   if (rc != ENS_OK || stage == ENS_STAGE_MIDDLE) return rc;
   rc = launch_decode_tc<ENS_LEVEL_FINE, 64, 1>(sc, pts, pts_is_f64, n, stage == ENS_STAGE_FINE ? apply_mask : 0, out4, s,
-                                               msave ? msave + mstride : nullptr);
+                                               msave ? msave + mstride : nullptr, rsave ? rsave + rstride : nullptr);
   if (rc != ENS_OK || stage == ENS_STAGE_FINE) return rc;
-  return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s, msave ? msave + 2 * mstride : nullptr);
+  return launch_decode_tc<ENS_LEVEL_COLOR, 32, 4>(sc, pts, pts_is_f64, n, apply_mask, out4, s, msave ? msave + 2 * mstride : nullptr,
+                                                  rsave ? rsave + 2 * rstride : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -559,10 +450,13 @@ static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P
   constexpr int ndec = (STAGE == ENS_STAGE_FINE) ? 2 : 3;
   TcMultiArgs m;
   m.base.sc = a.sc; m.base.pts = pts; m.base.n = P; m.base.out4 = nullptr; m.base.apply_mask = 0; m.base.msave = nullptr;
+  m.base.rsave = nullptr;
   m.base.separate = 1;
+  const int64_t rstride = ((P + 127) / 128) * TC_RSAVE_TILE_FLOATS;
   for (int d = 0; d < 3; ++d) {
     m.out[d] = planes + (int64_t)d * P * 4;
     m.msave[d] = a.save_masks ? a.save_masks + (int64_t)d * a.n_tiles * 160 : nullptr;
+    m.rsave[d] = a.save_r ? a.save_r + (int64_t)d * rstride : nullptr;
   }
   const size_t smem = (size_t)(MlpPackTC<64>::total() + 8 * 1024) * 4;       // the fine decoder's blob is the largest
   if (cudaFuncSetAttribute(decode_tc_multi_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
@@ -601,7 +495,8 @@ int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, c
     planes = reinterpret_cast<const float4 *>(pl);
     n_planes = ndec;
   } else {
-    const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s, a.save_masks, a.n_tiles * 160);
+    const int rc = tc_eval_points(a.sc, stage, pts, 1, P, 1, raw, s, a.save_masks, a.n_tiles * 160, a.save_r,
+                                  ((P + 127) / 128) * TC_RSAVE_TILE_FLOATS);
     if (rc != ENS_OK) return rc;
   }
   if (a.ra.R <= 4096 && a.ra.S <= ENS_MAX_SAMPLES)

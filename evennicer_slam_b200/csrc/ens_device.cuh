@@ -206,6 +206,7 @@ struct FwdArgs {
   uint32_t *save_masks;
   float *save_h;
   int64_t n_tiles;
+  float *save_r = nullptr;      // tcgen05 forward, saved kind 3: relu outputs [3 decoders][ceil(P/128)][5][128][32]
 };
 
 struct BwdArgs {
@@ -228,6 +229,7 @@ struct BwdArgs {
   float *split_gh;          // [3 decoders][n_tiles][5][1024]  g_h tiles
   uint32_t *split_mw;       // [3 decoders][n_tiles][5][32]    relu mask words per point
   float *split_pts;         // [n_tiles][32][8]                p.float(), valid, normalised coordinates
+  const float *save_r = nullptr;   // tcgen05 forward, saved kind 3 (see FwdArgs)
 };
 
 constexpr int NT_RENDER = 192;   // fma variant: 4 rays x 48 samples (6 x 32-sample rays)
@@ -273,7 +275,18 @@ int mma_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f
 int mma_render_fwd(FwdArgs &a, int stage, cudaStream_t s);
 // tcgen05 variant (ens_decode_tc.cu)
 int tc_eval_points(const DevScene &sc, int stage, const void *pts, int pts_is_f64, int64_t n, int apply_mask,
-                   float *out4, cudaStream_t s, uint32_t *msave = nullptr, int64_t mstride = 0);
+                   float *out4, cudaStream_t s, uint32_t *msave = nullptr, int64_t mstride = 0, float *rsave = nullptr,
+                   int64_t rstride = 0);
+constexpr int64_t TC_RSAVE_TILE_FLOATS = 5 * 128 * 32;     // r_0..r_4 of one 128-point tile of one decoder
+// bytes of the saved-for-backward buffer of the tcgen05 forward with decoder gradients (saved kind 3)
+inline int64_t tc_saved_r_bytes(int64_t n_rays, int S, int stage) {
+  if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
+  const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
+  return (int64_t)ndec * ((n_rays * S + 127) / 128) * TC_RSAVE_TILE_FLOATS * (int64_t)sizeof(float);
+}
+// tcgen05 backward (ens_bwd_tc.cu)
+int tc_render_bwd(BwdArgs &a, int stage, bool wg, void *workspace, int64_t workspace_bytes, cudaStream_t s);
+int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage);
 int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s);
 int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage);
 int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset);

@@ -223,7 +223,50 @@ __device__ __forceinline__ void pack_mlp_tc_body(const PtrTable &t, float *__res
   out[idx] = v;
 }
 
-// one launch packs all sections of a decoder blob (fma | mma forward | mma backward | tcgen05)
+// tcgen05 backward layout (see MlpPackTCB): transposed matrices, canonical K-major (K = 32 output units), value + remainder
+template <int CD, int NO>
+__device__ __forceinline__ void pack_mlp_tcb_body(const PtrTable &t, float *__restrict__ out, int idx) {
+  using P = MlpPackTCB;
+  auto Wh = [&](int i, int n, int j) { return (i == 3) ? t.p[11 + 2 * 3][n * 125 + EMB + j] : t.p[11 + 2 * i][n * 32 + j]; };
+  float v = 0.f;
+  if (idx < 2 * P::TOT()) {
+    const bool lo = idx >= P::TOT();
+    int o = lo ? idx - P::TOT() : idx;
+    int mat, i = 0;
+    if (o < P::off_MT(0)) { mat = 0; i = 1 + o / 1024; o %= 1024; }
+    else if (o < P::off_W0T()) { mat = 1; o -= P::off_MT(0); i = o / 1024; o %= 1024; }
+    else if (o < P::off_W3eT()) { mat = 2; o -= P::off_W0T(); }
+    else { mat = 3; o -= P::off_W3eT(); }
+    // canonical [rows][K = 32]: row group of 8 = 256 floats, k group of 4 = 32 floats
+    const int ri = o / 256, r1 = o % 256;
+    const int ki = r1 / 32, r2 = r1 % 32;
+    const int row = ri * 8 + r2 / 4, n = ki * 4 + r2 % 4;            // row = input index of the layer, n = output unit
+    float w = 0.f;
+    if (mat == 0) w = Wh(i, n, row);
+    else if (mat == 1) {                                            // M_i[n][row] = sum_j Wh_{i+1}[n][j] Wc_i[j][row]
+      double acc = 0.0;
+      for (int j = 0; j < 32; ++j) acc += (double)Wh(i + 1, n, j) * (double)t.p[2 * i][j * CD + row];
+      w = (float)acc;
+    } else if (mat == 2) w = (row < EMB) ? t.p[11][n * EMB + row] : 0.f;
+    else w = (row < EMB) ? t.p[11 + 2 * 3][n * 125 + row] : 0.f;
+    const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+    v = lo ? (w - hi) : w;
+  } else {
+    int o = idx - P::off_B();
+    if (o < 3 * EMBP) { int r = o / EMBP, k = o % EMBP; v = (k < EMB) ? t.p[10][r * EMB + k] : 0.f; }
+    else if (o < 3 * EMBP + 128) { o -= 3 * EMBP; int n = o / 32, j = o % 32; v = (n < NO) ? t.p[21][n * 32 + j] : 0.f; }
+    else {                                                          // MoF[q][k] = sum_j Wo[q][j] Wc_4[j][k], k < 32
+      o -= 3 * EMBP + 128;
+      const int q = o / 32, k = o % 32;
+      double acc = 0.0;
+      if (q < NO) for (int j = 0; j < 32; ++j) acc += (double)t.p[21][q * 32 + j] * (double)t.p[2 * 4][j * CD + k];
+      v = (float)acc;
+    }
+  }
+  out[idx] = v;
+}
+
+// one launch packs all sections of a decoder blob (fma | mma forward | mma backward | tcgen05 | tcgen05 backward)
 template <int CD, int NO>
 __global__ void pack_mlp_all_kernel(PtrTable t, float *__restrict__ out) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,7 +276,9 @@ __global__ void pack_mlp_all_kernel(PtrTable t, float *__restrict__ out) {
   idx -= MlpPackV2<CD>::total();
   if (idx < MlpPackV2B::total()) { pack_mlp_v2b_body<CD, NO>(t, out + off_v2b<CD>(), idx); return; }
   idx -= MlpPackV2B::total();
-  if (idx < MlpPackTC<CD>::total()) pack_mlp_tc_body<CD, NO>(t, out + off_tc<CD>(), idx);
+  if (idx < MlpPackTC<CD>::total()) { pack_mlp_tc_body<CD, NO>(t, out + off_tc<CD>(), idx); return; }
+  idx -= MlpPackTC<CD>::total();
+  if (idx < MlpPackTCB::total()) pack_mlp_tcb_body<CD, NO>(t, out + off_tcb<CD>(), idx);
 }
 
 __global__ void pack_coarse_kernel(PtrTable t, float *__restrict__ out) {

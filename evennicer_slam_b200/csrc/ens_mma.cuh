@@ -340,6 +340,77 @@ __device__ __forceinline__ void gather_warp(const float *__restrict__ grid, cons
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// trilinear backward for the warp's 32 points.  crow: the warp's feature-tile rows; columns 0..31 hold the
+// feature gradient g_c (swizzled) -- written by store_tile just before.  8 lanes per point.
+//   ggrid != null : scatter  w_corner * g_c  into the native-layout gradient grid (valid points only)
+//   want_coord    : gpn = d L / d (normalised coords) of the owner lane's point
+// ---------------------------------------------------------------------------------------------
+template <int RS>
+__device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, float *__restrict__ ggrid,
+                                                const int dims[3], const Vox &v, bool valid,
+                                                const float *__restrict__ crow, bool want_coord, float (&gpn)[3]) {
+  const int lane = threadIdx.x & 31;
+  const int X = dims[2], Y = dims[1], Z = dims[0];
+  const int base = ((v.z0 * Y + v.y0) * X + v.x0) * C;
+  const bool okx = v.x0 + 1 < X, oky = v.y0 + 1 < Y, okz = v.z0 + 1 < Z;
+  const unsigned okbits = (unsigned)okx | ((unsigned)oky << 1) | ((unsigned)okz << 2) | ((unsigned)valid << 3);
+  const int cq = lane & 7, pp = lane >> 3;
+  const int sx = C, sy = X * C, sz = X * Y * C;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+#pragma unroll 1
+  for (int grp = 0; grp < 8; ++grp) {
+    const int src = 4 * grp + pp;
+    const int b = __shfl_sync(0xffffffffu, base, src);
+    const float fx1 = __shfl_sync(0xffffffffu, v.fx, src), fx0 = __shfl_sync(0xffffffffu, v.gx, src);
+    const float fy1 = __shfl_sync(0xffffffffu, v.fy, src), fy0 = __shfl_sync(0xffffffffu, v.gy, src);
+    const float fz1 = __shfl_sync(0xffffffffu, v.fz, src), fz0 = __shfl_sync(0xffffffffu, v.gz, src);
+    const unsigned okb = __shfl_sync(0xffffffffu, okbits, src);
+    const int ox = (okb & 1u) ? sx : 0, oy = (okb & 2u) ? sy : 0, oz = (okb & 4u) ? sz : 0;
+    const float4 gc = *reinterpret_cast<const float4 *>(crow + src * RS + ((4 * cq) ^ ((src & 3) << 3)));
+    const int off0 = b + 4 * cq;
+    float gix = 0.f, giy = 0.f, giz = 0.f;
+    float4 a[8];
+    if (want_coord) {       // all eight corner lines in flight before the first use (addresses are always valid)
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        a[c] = __ldg(reinterpret_cast<const float4 *>(grid + off0 + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0)));
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool inr = (!(c & 1) || (okb & 1u)) && (!(c & 2) || (okb & 2u)) && (!(c & 4) || (okb & 4u));
+      const int off = off0 + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0);
+      const float wx = (c & 1) ? fx1 : fx0, wy = (c & 2) ? fy1 : fy0, wz = (c & 4) ? fz1 : fz0;
+      if (inr) {
+        if (ggrid != nullptr && (okb & 8u)) {
+          const float w = __fmul_rn(__fmul_rn(wx, wy), wz);
+          if (w != 0.f) red_add_v4(ggrid + off, w * gc.x, w * gc.y, w * gc.z, w * gc.w);
+        }
+        if (want_coord) {
+          const float dot = fmaf(a[c].w, gc.w, fmaf(a[c].z, gc.z, fmaf(a[c].y, gc.y, a[c].x * gc.x)));
+          gix += ((c & 1) ? 1.f : -1.f) * wy * wz * dot;
+          giy += ((c & 2) ? 1.f : -1.f) * wx * wz * dot;
+          giz += ((c & 4) ? 1.f : -1.f) * wx * wy * dot;
+        }
+      }
+    }
+    if (want_coord) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, o);
+        giy += __shfl_xor_sync(0xffffffffu, giy, o);
+        giz += __shfl_xor_sync(0xffffffffu, giz, o);
+      }
+      // point 4*grp + pp was handled by lanes 8pp..8pp+7: deliver to its owner lane
+      const float ax = __shfl_sync(0xffffffffu, gix, 8 * (lane & 3));
+      const float ay = __shfl_sync(0xffffffffu, giy, 8 * (lane & 3));
+      const float az = __shfl_sync(0xffffffffu, giz, 8 * (lane & 3));
+      if ((lane >> 2) == grp) { mx = ax; my = ay; mz = az; }
+    }
+  }
+  gpn[0] = mx * v.sx; gpn[1] = my * v.sy; gpn[2] = mz * v.sz;
+}
+
 // Copy a packed weight blob global -> shared with cp.async (LDGSTS, 16 bytes per lane, no register round trip):
 // all copies of the CTA are in flight at once; the caller's __syncthreads() (after stage_blob_wait) publishes them.
 __device__ __forceinline__ void stage_blob(float *__restrict__ sw, const float *__restrict__ gw, int nfloats) {

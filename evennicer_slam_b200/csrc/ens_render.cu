@@ -946,8 +946,17 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   fill_ray_args(a.ra, cfg, stage, rays_o, rays_d, gt_depth, depth_max, n_rays, S, ns);
   a.depth = depth; a.var = var; a.color = color; a.z_out = z_vals; a.w_out = weights; a.raw_out = raw;
   a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0;
-  if (saved_with_activations < 0 || saved_with_activations > 2) return ENS_EINVAL;
+  if (saved_with_activations < 0 || saved_with_activations > 3) return ENS_EINVAL;
   const bool want_h = saved_with_activations == 1;
+  if (saved_with_activations == 3) {
+    // tcgen05 forward that keeps the relu outputs r_0..r_4 of every decoder: the forward of the tcgen05 backward WITH
+    // decoder gradients (mapping).  Anything that prevents this path is an error (no silent change of format).
+    const int64_t need = tc_saved_r_bytes(n_rays, S, stage);
+    if (need <= 0 || saved == nullptr || !use_mma_forward()) return ENS_EUNSUPPORTED;
+    if (saved_bytes < need || (reinterpret_cast<uintptr_t>(saved) & 15)) return ENS_ESHAPE;
+    a.save_r = reinterpret_cast<float *>(saved);
+    return tc_render_fwd(a, stage, scratch, scratch_bytes, (cudaStream_t)stream);
+  }
   if (saved != nullptr) {
     int64_t n_tiles = 0, h_off = 0;
     const int64_t need = mma_fwd_saved_bytes(n_rays, S, stage, want_h, &n_tiles, &h_off);
@@ -991,16 +1000,31 @@ extern "C" int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int 
   return mma_fwd_saved_bytes(n_rays, n_samples_total, stage, want_decoder_grads, nullptr, nullptr);
 }
 
+extern "C" int64_t ens_fwd_saved_bytes_kind(int64_t n_rays, int n_samples_total, int stage, int kind) {
+  if (kind == 3) return use_mma_forward() ? tc_saved_r_bytes(n_rays, n_samples_total, stage) : 0;
+  if (kind < 0 || kind > 3) return 0;
+  return ens_fwd_saved_bytes(n_rays, n_samples_total, stage, kind == 1);
+}
+
 extern "C" int64_t ens_fwd_scratch_bytes(int64_t n_rays, int n_samples_total, int stage) {
   if (!use_mma_forward()) return 0;
   return tc_fwd_scratch_bytes(n_rays, n_samples_total, stage);
 }
 
+// tcgen05 backward (default for saved kinds 2 and 3); ENS_BWD_TC=0 keeps the mma.sync kernels for kind 2 (A/B check)
+static bool use_tc_backward() {
+  const char *v = std::getenv("ENS_BWD_TC");
+  return !(v && v[0] == '0');
+}
+
 extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads) {
-  if (!want_decoder_grads || n_rays <= 0 || n_samples_total <= 0) return 0;
+  if (n_rays <= 0 || n_samples_total <= 0) return 0;
+  const int64_t tc = tc_bwd_workspace_bytes(n_rays, n_samples_total, ENS_STAGE_COLOR);
+  if (!want_decoder_grads) return tc;
   const int64_t fma = (n_rays * (int64_t)n_samples_total + 1) * 160 * (int64_t)sizeof(float);   // +1: dump row for idle lanes
   const int64_t mma = mma_bwd_workspace_bytes(n_rays, n_samples_total);
-  return fma > mma ? fma : mma;
+  const int64_t m = fma > mma ? fma : mma;
+  return m > tc ? m : tc;
 }
 
 extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
@@ -1039,7 +1063,14 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   a.g_rays_o = grads->rays_o; a.g_rays_d = grads->rays_d;
   a.hscratch = (float *)workspace;
   a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0; a.mask_fmt = 0;
-  if (saved_with_activations < 0 || saved_with_activations > 2) return ENS_EINVAL;
+  if (saved_with_activations < 0 || saved_with_activations > 3) return ENS_EINVAL;
+  if (saved_with_activations == 3) {          // relu outputs kept by the tcgen05 forward: tcgen05 backward with decoder gradients
+    const int64_t need = tc_saved_r_bytes(n_rays, S, stage);
+    if (need <= 0 || saved == nullptr) return ENS_EUNSUPPORTED;
+    if (saved_bytes < need) return ENS_ESHAPE;
+    a.save_r = reinterpret_cast<const float *>(saved);
+    return tc_render_bwd(a, stage, wg, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
   const bool have_h = saved_with_activations == 1;
   if (saved_with_activations == 2 && (saved == nullptr || !use_mma_backward())) return ENS_EUNSUPPORTED;
   if (saved != nullptr && use_mma_backward()) {
@@ -1062,6 +1093,11 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   // with saved activations the workspace is optional: given (and large enough) it enables the split backward
   if (wg && saved_covers && (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1))) a.hscratch = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
+  if (saved_with_activations == 2 && !wg && use_tc_backward() && workspace != nullptr &&
+      workspace_bytes >= tc_bwd_workspace_bytes(n_rays, S, stage)) {
+    rc = tc_render_bwd(a, stage, false, workspace, workspace_bytes, s);
+    if (rc != ENS_EUNSUPPORTED) return rc;
+  }
   if (use_mma_backward()) {
     rc = mma_render_bwd(a, stage, wg, s);
     if (rc != ENS_EUNSUPPORTED) return rc;       // coarse stage: fma kernels below

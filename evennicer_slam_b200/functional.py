@@ -19,6 +19,7 @@ from .scene import SceneCache, build_scene_struct, decoder_grad_views, is_native
 TC_MIN_POINTS = 1         # every forward-only call takes the placement + tcgen05 decode + compositing path (one variant for all
                           # batch sizes keeps the forward bit-independent of how a frame is cut into batches)
 TC_POSE_FORWARD = os.environ.get("ENS_FWD_TC_MASKS", "1") != "0"   # tcgen05 forward when only masks are kept
+TC_MAP = os.environ.get("ENS_MAP_TC", "1") != "0"   # tcgen05 forward + backward when decoder gradients are wanted (saved kind 3)
 SAVE_FORWARD = True    # keep relu masks / activations from the forward kernel for the backward (False: it recomputes)
 _DEBUG: Dict[str, object] = {}     # test hook: set _DEBUG["keep_workspace"]=True to inspect the backward scratch
 
@@ -146,20 +147,30 @@ class _RenderBatchRay(torch.autograd.Function):
         want_bwd = any(needs[6:])
         want_dec = want_bwd and any(needs[8 + n_grids:])
         saved = None
-        saved_kind = 1 if want_dec else 0          # 0: relu masks, 1: masks + activations, 2: masks from the tcgen05 forward
-        if want_bwd and SAVE_FORWARD:
+        # 0: relu masks, 1: masks + activations (mma.sync kernels), 2: masks from the tcgen05 forward,
+        # 3: relu outputs from the tcgen05 forward (tcgen05 backward with decoder gradients)
+        saved_kind = 1 if want_dec else 0
+        tc_map = want_dec and TC_MAP and SAVE_FORWARD and setup.stage != "coarse"
+        if tc_map:
+            nbytes = int(L.ens_fwd_saved_bytes_kind(R, S, STAGES[setup.stage], 3))
+            if nbytes > 0:
+                saved = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
+                saved_kind = 3
+            else:
+                tc_map = False
+        if want_bwd and SAVE_FORWARD and not tc_map:
             nbytes = int(L.ens_fwd_saved_bytes(R, S, STAGES[setup.stage], int(want_dec)))
             if nbytes > 0:
                 saved = torch.empty(nbytes // 4, dtype=torch.int32, device=dev)
         scratch = None
-        tc_forward = (not want_bwd) or (saved is not None and not want_dec and TC_POSE_FORWARD)
+        tc_forward = (not want_bwd) or tc_map or (saved is not None and not want_dec and TC_POSE_FORWARD)
         if tc_forward and R * S >= TC_MIN_POINTS:
             # no activations to keep (forward only: render_img, visualisation; or a backward without decoder gradients:
             # tracking, the tracker's event render): scratch for the placement -> tcgen05 decode -> compositing path
             nbytes = int(L.ens_fwd_scratch_bytes(R, S, STAGES[setup.stage]))
             if nbytes > 0:
                 scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
-                if saved is not None:
+                if saved is not None and not tc_map:
                     saved_kind = 2
         stream = _lib.cur_stream(dev)
         _lib.check(TIMER.launch("render_fwd", dev, lambda: L.ens_render_fwd(

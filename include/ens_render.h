@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ENS_ABI_VERSION 4
+#define ENS_ABI_VERSION 5
 
 typedef void *ens_stream_t; /* cudaStream_t */
 
@@ -95,12 +95,17 @@ int64_t ens_packed_decoder_floats(int level);
 int64_t ens_decoder_grad_floats(int level);
 /* number of tensors in a decoder's state_dict (22 for coarse-less MLPs: 10 fc_c + _B + 10 pts + 2 out = 23; 12 coarse) */
 int ens_decoder_num_tensors(int level);
-/* bytes of scratch ens_render_bwd needs for R rays x S samples when decoder grads are requested */
+/* bytes of scratch ens_render_bwd needs for R rays x S samples (the tcgen05 backward keeps the sample points, the
+ * per-point output gradients, d L / d p and the folded weight-gradient sums there) */
 int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads);
 /* bytes of the saved-for-backward buffer ens_render_fwd can fill (relu masks, plus the hidden activations when
  * decoder gradients will be wanted) so that ens_render_bwd does not recompute the forward -- what torch autograd
  * keeps as saved tensors in the reference.  0 = not applicable for this stage / sample count (pass NULL). */
 int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int stage, int want_decoder_grads);
+/* the same by saved kind (the saved_with_activations argument of ens_render_fwd / ens_render_bwd): 0, 1 as above; 2 = relu
+ * masks written by the tcgen05 forward; 3 = the relu outputs r_0..r_4 of every decoder written by the tcgen05 forward
+ * (640 B per point and decoder) -- what the tcgen05 backward needs for the decoder gradients. */
+int64_t ens_fwd_saved_bytes_kind(int64_t n_rays, int n_samples_total, int stage, int kind);
 /* bytes of optional scratch for a forward that will NOT be followed by a backward (render_img, visualisation): with it
  * ens_render_fwd runs sample placement, the tcgen05 decode and the compositing as separate kernels over per-point
  * arrays in this scratch (faster for large batches); without it the fused kernel is used.  0 = not applicable. */
@@ -165,7 +170,9 @@ int ens_eval_points(const EnsScene *scene, int stage, const void *pts, int pts_i
  * filled for ens_render_bwd (16-byte aligned; NULL = the backward recomputes).
  * saved_with_activations: 0 = relu masks only (enough for a backward without decoder gradients), 1 = masks + hidden
  * activations (decoder gradients), 2 = masks only, written by the tcgen05 decode path (placement -> decode -> compositing;
- * needs `scratch`; ENS_EUNSUPPORTED if that path cannot run) -- pass the same value to ens_render_bwd.
+ * needs `scratch`; ENS_EUNSUPPORTED if that path cannot run), 3 = relu outputs of every block, written by the tcgen05
+ * decode path (needs `scratch`; the forward of the tcgen05 backward with decoder gradients) -- pass the same value to
+ * ens_render_bwd.
  * scratch / scratch_bytes: optional, see ens_fwd_scratch_bytes (used when saved is NULL or saved_with_activations == 2). */
 int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, int stage, const float *rays_o,
                    const float *rays_d, const float *gt_depth, const double *depth_max, int64_t n_rays,
