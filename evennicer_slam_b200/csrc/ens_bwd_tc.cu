@@ -480,6 +480,403 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(TCOLS) : "memory");
 }
 
+
+// =============================================================================================================
+// Backward WITH decoder gradients: 8 warps.  Warps 0..3 ("E") own the TMEM lanes: g_u_i, bias sums, N-side staging,
+// the A operand, the tail.  Warps 4..7 ("H", warp 4 + w on the same SM sub-partition as E warp w and working on the same 32
+// points) own the M-side: features, relu outputs from the forward, Fourier chunks; warp 4 issues every MMA.  All threads walk
+// the same sequence of weight-gradient passes; before staging for pass p a thread waits for the MMAs of pass p - 1 (barW),
+// E additionally for the data-gradient MMAs of the current block (barD, committed before the weight-gradient MMAs are
+// issued) -- so the weight-gradient GEMM of a pass overlaps the E warps' work on the next block and the H warps'
+// global loads / sines for the next pass.
+//   passes (accumulator = pass):  0 L4 [r3|c]  1 L3 [r2|c]  2 L3 [e0|e1]  3 L3 [e2|c]  4 L2 [r1|c]  5 L1 [r0|c]  6 L0 [e0|c]  7 L0 [e1|e2]
+//   FINE_CM: five passes 0..4 = blocks 4..0, slot B = the middle-level features, slot A unused.
+// =============================================================================================================
+__device__ __forceinline__ void cta_sync256() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void load_row32(const float *__restrict__ src, float (&v)[32]) {
+  const float4 *s4 = reinterpret_cast<const float4 *>(src);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { const float4 x = __ldg(s4 + q); v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_raw) {
+  constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
+  constexpr int CD = (LEVEL == ENS_LEVEL_FINE) ? 64 : 32;
+  constexpr int NO = (ROLE == ROLE_COLOR) ? 3 : 1;
+  constexpr int DEC = (ROLE == ROLE_MIDDLE) ? 0 : (ROLE == ROLE_COLOR ? 2 : 1);
+  constexpr bool TAIL = ROLE != ROLE_FINE_CM;
+  constexpr int CLEVEL = (ROLE == ROLE_FINE_CM) ? ENS_LEVEL_MIDDLE : LEVEL;
+  constexpr int NPASS = TAIL ? 8 : 5;
+  using PB = MlpPackTCB;
+
+  float *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) / 4;
+  float *sMB = base;                 // hiA, hiB, loA, loB
+  float *sNB = base + 16384;         // g_hi, g_lo
+  float *sw = sNB + 8192;
+  __shared__ __align__(8) uint64_t barD, barW;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float4 sP[128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool isE = warp < 4;
+  const int pl = tid & 127;          // point of the tile this thread works on
+  const int w4 = warp & 3;
+
+  {
+    const float *gw = a.sc.w[LEVEL] + off_tcb<CD>();
+    const uint32_t s0 = smem_u32(sw);
+    for (int i = tid; i < PB::total() / 4; i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&barD)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&barW)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb0 = tmem_base_s;
+  const uint32_t tb = tb0 + ((uint32_t)(32 * w4) << 16);
+  const uint32_t swb = smem_u32(sw), sMBa = smem_u32(sMB), sNBa = smem_u32(sNB);
+  uint32_t pw = 0, pd = 0;           // phase parities of barW / barD as this thread has consumed them
+  bool first = true;                 // no weight-gradient pass has been issued yet
+
+  if (isE) {      // zero the weight-gradient accumulators
+    uint32_t zz[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) zz[k] = 0u;
+#pragma unroll 1
+    for (int c = 0; c < NPASS; ++c) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                   "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+                   "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                   :: "r"(tb + TB_ACC + 32 * c), "r"(zz[0]), "r"(zz[1]), "r"(zz[2]), "r"(zz[3]), "r"(zz[4]), "r"(zz[5]), "r"(zz[6]), "r"(zz[7]),
+                     "r"(zz[8]), "r"(zz[9]), "r"(zz[10]), "r"(zz[11]), "r"(zz[12]), "r"(zz[13]), "r"(zz[14]), "r"(zz[15]),
+                     "r"(zz[16]), "r"(zz[17]), "r"(zz[18]), "r"(zz[19]), "r"(zz[20]), "r"(zz[21]), "r"(zz[22]), "r"(zz[23]),
+                     "r"(zz[24]), "r"(zz[25]), "r"(zz[26]), "r"(zz[27]), "r"(zz[28]), "r"(zz[29]), "r"(zz[30]), "r"(zz[31])
+                   : "memory");
+    }
+    tmem_st_done();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // sums that live in registers across the CTA's tiles (lane k = column k; one partial per warp)
+  float bhat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float dBacc[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float dwor[NO], qo[NO], dbo[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) dwor[o] = qo[o] = dbo[o] = 0.f;
+
+  const bool want_rays = TAIL && a.gp != nullptr;
+  const int nctas = a.ctas[ROLE];
+  // the layer of a pass (-1: Fourier-chunk pass without data gradients)
+  auto pass_layer = [](int p) { return TAIL ? (p == 0 ? 4 : (p == 1 ? 3 : (p == 4 ? 2 : (p == 5 ? 1 : (p == 6 ? 0 : -1))))) : 4 - p; };
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+    const int64_t pt = tile * 128 + pl;
+    const bool valid = pt < a.P;
+    double p[3] = {0.0, 0.0, 0.0};
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const double *pp = a.pts + pt * 3;
+      p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
+      g4 = a.gout[pt];
+    }
+    float pn[3], p32[3];
+    normalize64(p, a.sc.lo, a.sc.hi, pn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p32[k] = __double2float_rn(p[k]);
+    float go[NO];
+    if (ROLE == ROLE_COLOR) { go[0] = g4.x; if (NO > 1) { go[1 % NO] = g4.y; go[2 % NO] = g4.z; } }
+    else go[0] = g4.w;
+    const float *rbase = a.save_r + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
+
+    if (isE) {
+      // ================================ E warps ================================
+      const Vox vox = make_vox(pn, a.sc.dims[LEVEL]);
+      uint32_t mw[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        mw[i] = valid ? __ldg(a.save_m + (int64_t)DEC * a.m_stride + (pt >> 5) * 160 + i * 32 + (pt & 31)) : 0u;
+      float g[32];
+      {
+        const float *Wo = sw + PB::off_Wo();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float s = 0.f;
+#pragma unroll
+          for (int o = 0; o < NO; ++o) s = fmaf(Wo[o * 32 + k], go[o], s);
+          g[k] = s;
+        }
+      }
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int i = pass_layer(ps);
+        if (i >= 0) {
+          uint32_t m = 0u;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) if (k == i) m = mw[k];
+          float gu[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) gu[k] = ((m >> k) & 1u) ? g[k] : 0.f;
+          const float bs = warp_colsum32(gu);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) if (k == i) bhat[k] += bs;
+          if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+          stage_row(sNB, sNB + 4096, pl, gu);
+          if (i >= 1 || TAIL) tmem_st32_split(tb + TB_XH, tb + TB_XL, gu);
+          tmem_st_done();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        } else {
+          if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+        }
+        first = false;
+        tc_fence_before();
+        cta_sync256();
+        if (i >= 1) {
+          mbar_wait(&barD, pd); pd ^= 1;
+          tc_fence_after();
+          tmem_ld32(tb + TB_DH, g);
+        } else if (i == 0 && TAIL) {
+          mbar_wait(&barD, pd); pd ^= 1;              // g_e complete
+          tc_fence_after();
+        }
+      }
+      // ---- tail: feature gradient -> grid scatter + coordinate gradient; embedding gradient ----
+      if (TAIL) {
+        mbar_wait(&barW, pw); pw ^= 1;                // last pass done: the N-side block doubles as this warp's 32x32 tile
+        first = true;                                 // ... and that wait already consumed the phase the next tile would wait for
+        tc_fence_after();
+        float *stile = sNB + w4 * 1024;
+        sP[pl] = make_float4(p32[0], p32[1], p32[2], 0.f);
+        double gp[3] = {0.0, 0.0, 0.0};
+        float *ggrid = a.ggrid[LEVEL];
+        if (ggrid != nullptr || want_rays) {
+          float gc[32];
+          tmem_ld32(tb + TB_DC, gc);
+          const float *MoF = sw + PB::off_MoF();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float s = gc[k];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) s = fmaf(MoF[o * 32 + k], go[o], s);
+            gc[k] = s;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
+          __syncwarp();
+          float gpn[3];
+          gather_bwd_warp<32>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], vox, valid, stile, want_rays, gpn);
+          if (want_rays) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gp[k] += __ddiv_rn((double)gpn[k] * 2.0, __dsub_rn(a.sc.hi[k], a.sc.lo[k]));
+          }
+          __syncwarp();
+        }
+        {
+          const float *B = sw + PB::off_B();
+          float gpe[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int jc = 0; jc < 3; ++jc) {
+            float ge[32];
+            tmem_ld32(tb + TB_DE + 32 * jc, ge);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float bx = B[32 * jc + k], by = B[EMBP + 32 * jc + k], bz = B[2 * EMBP + 32 * jc + k];
+              float sq, cq;
+              fast_sincos(fmaf(p32[2], bz, fmaf(p32[1], by, p32[0] * bx)), sq, cq);
+              const float gq = ge[k] * cq;
+              ge[k] = gq;
+              gpe[0] = fmaf(bx, gq, gpe[0]); gpe[1] = fmaf(by, gq, gpe[1]); gpe[2] = fmaf(bz, gq, gpe[2]);
+            }
+            // dB[r][32 jc + k] = sum_pt p[pt][r] g_q[pt][k]: transpose through the warp's tile, lane k walks its column
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float v = stile[r * 32 + (lane ^ ((r & 3) << 3))];
+              const float4 pr = sP[32 * w4 + r];
+              s0 = fmaf(pr.x, v, s0); s1 = fmaf(pr.y, v, s1); s2 = fmaf(pr.z, v, s2);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q == jc) { dBacc[q][0] += s0; dBacc[q][1] += s1; dBacc[q][2] += s2; }
+            __syncwarp();
+          }
+          if (want_rays) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gp[k] += (double)gpe[k];
+          }
+        }
+        if (want_rays && valid) {
+          float *dst = a.gp + ((int64_t)DEC * a.P + pt) * 3;
+          dst[0] = (float)gp[0]; dst[1] = (float)gp[1]; dst[2] = (float)gp[2];
+        }
+        tc_fence_before();
+      }
+    } else {
+      // ================================ H warps ================================
+      float c[32], rn[32];
+      if (TAIL) {
+        load_row32(rbase + 4 * 4096, rn);                         // r_4
+        // output layer sums: sum g_out[o] r_4[k], sum g_out[o]
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          float t[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = go[o] * rn[k];
+          dwor[o] += warp_colsum32(t);
+          float sg = go[o];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, off);
+          dbo[o] += sg;
+        }
+        load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0 (in flight during the gather)
+      }
+      const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
+      if (!first) { mbar_wait(&barW, pw); pw ^= 1; }              // the previous tile's last pass: the M-side blocks are free
+      {
+        // features straight into slot B: gather_warp's tile layout IS the MN-major swizzle (32-byte chunk ^ (row & 3))
+        float *tileB = sMB + 4096 + w4 * 1024;
+        __syncwarp();
+        gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
+        float *lrow = sMB + 3 * 4096 + w4 * 1024 + lane * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int off = (4 * q) ^ ((lane & 3) << 3);
+          const float4 x = *reinterpret_cast<const float4 *>(tileB + lane * 32 + off);
+          c[4 * q] = x.x; c[4 * q + 1] = x.y; c[4 * q + 2] = x.z; c[4 * q + 3] = x.w;
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          *reinterpret_cast<float4 *>(lrow + off) = l;
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          float t[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = go[o] * c[k];
+          qo[o] += warp_colsum32(t);
+        }
+      }
+      const float *B = sw + PB::off_B();
+      auto fourier = [&](int jc, float (&e)[32]) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          e[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * jc + k], fmaf(p32[1], B[EMBP + 32 * jc + k], p32[0] * B[32 * jc + k])));
+      };
+      bool waited = true;       // the M-side blocks are free (the wait above)
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int i = pass_layer(ps);
+        if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }
+        waited = false;
+        first = false;
+        if (TAIL) {
+          if (i >= 1) stage_row(sMB, sMB + 2 * 4096, pl, rn);                    // slot A = r_{i-1}
+          else if (i == 0) { float e[32]; fourier(0, e); stage_row(sMB, sMB + 2 * 4096, pl, e); }
+          else if (ps == 2) {
+            float e[32];
+            fourier(0, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
+            fourier(1, e); stage_row(sMB + 4096, sMB + 3 * 4096, pl, e);
+          } else if (ps == 3) {
+            float e[32];
+            fourier(2, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
+            stage_row(sMB + 4096, sMB + 3 * 4096, pl, c);                        // the features back into slot B
+          } else {
+            float e[32];
+            fourier(1, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
+            fourier(2, e); stage_row(sMB + 4096, sMB + 3 * 4096, pl, e);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        cta_sync256();
+        if (warp == 4) {
+          tc_fence_after();
+          if (i >= 1) {
+            issue_gemm<32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_WhT(1) + (i - 1) * 1024, PB::TOT(), 0u);
+            if (TAIL) issue_gemm<32, 32>(tb0 + TB_DC, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_MT(0) + (i - 1) * 1024, PB::TOT(), i == 4 ? 0u : 1u);
+          }
+          if (TAIL && (i == 3 || i == 0))
+            issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, i == 3 ? PB::off_W3eT() : PB::off_W0T(), PB::TOT(), i == 3 ? 0u : 1u);
+          if (i >= 1 || (i == 0 && TAIL)) umma_commit(&barD);
+          issue_wgrad(tb0 + TB_ACC + 32 * ps, sMBa, sNBa);
+          umma_commit(&barW);
+          __syncwarp();
+        }
+        // the next main pass's slot A: r_{i-2}, fetched while this pass's MMAs run
+        if (TAIL) {
+          const int nxt = (ps + 1 < NPASS) ? pass_layer(ps + 1) : -1;
+          if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
+        }
+      }
+    }
+  }
+
+  // ---- flush the CTA's sums ----
+  if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+  tc_fence_after();
+  float *raw = a.raw_acc + (int64_t)ROLE * RAW_FLOATS;
+  if (isE) {
+#pragma unroll 1
+    for (int acc = 0; acc < NPASS; ++acc) {
+      float v[32];
+      tmem_ld32(tb + TB_ACC + 32 * acc, v);
+      float *dst = raw + acc * 2048 + (pl & 63) * 32;               // lanes 64..127 hold the remainder products of rows 0..63
+#pragma unroll
+      for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
+    if (TAIL) {
+#pragma unroll
+      for (int jc = 0; jc < 3; ++jc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) atomicAdd(raw + RAW_DB + r * 96 + 32 * jc + lane, dBacc[jc][r]);
+    }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      atomicAdd(raw + RAW_DWOR + o * 32 + lane, dwor[o]);
+      atomicAdd(raw + RAW_QO + o * 32 + lane, qo[o]);
+      if (lane == 0) atomicAdd(raw + RAW_DBO + o, dbo[o]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(512u) : "memory");
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(256, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  const int role = blockIdx.y;
+  if ((int)blockIdx.x >= a.ctas[role]) return;
+  if (role == ROLE_MIDDLE) bwd_tc_wg_body<ROLE_MIDDLE>(a, smem);
+  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE>(a, smem); }
+  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_wg_body<ROLE_COLOR>(a, smem); }
+  else { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE_CM>(a, smem); }
+}
+
 template <int STAGE, bool WG>
 __global__ void __launch_bounds__(128, 1) bwd_tc_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
@@ -488,7 +885,6 @@ __global__ void __launch_bounds__(128, 1) bwd_tc_kernel(BwdTcArgs a) {
   if (role == ROLE_MIDDLE) bwd_tc_body<ROLE_MIDDLE, WG>(a, smem);
   else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE, WG>(a, smem); }
   else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_body<ROLE_COLOR, WG>(a, smem); }
-  else { if constexpr (WG && STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE_CM, true>(a, smem); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +982,7 @@ __device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const
                                             const float *__restrict__ blob, float *__restrict__ gdec) {
   using PK = MlpPack<CD>;
   using GO = MlpGrad<CD, NOF>;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nt = gridDim.y * blockDim.x;
   auto accS = [](int i) { return i == 4 ? 0 : (i == 3 ? 1 : (i == 2 ? 4 : 5)); };                  // i = 1..4
   auto S = [&](int i, int n, int k) { return raw[accS(i) * 2048 + k * 32 + n]; };
   auto Q = [&](int i, int n, int ch) {                                                             // i = 0..4
@@ -604,17 +1000,17 @@ __device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const
   // fc_c.i.weight [32][CD], fc_c.i.bias [32]
   for (int idx = tid; idx < 5 * 32 * CD; idx += nt) {
     const int i = idx / (32 * CD), k = (idx / CD) % 32, ch = idx % CD;
-    double s = 0.0;
-    if (i < 4) { for (int n = 0; n < 32; ++n) s += (double)Wh(i + 1, n, k) * (double)Q(i + 1, n, ch); }
-    else { for (int o = 0; o < NO; ++o) s += (double)Wo(o, k) * (double)Qo(o, ch); }
-    gdec[GO::off_Wc(i) + k * CD + ch] += (float)s;
+    float s = 0.f;
+    if (i < 4) { for (int n = 0; n < 32; ++n) s = fmaf(Wh(i + 1, n, k), Q(i + 1, n, ch), s); }
+    else { for (int o = 0; o < NO; ++o) s = fmaf(Wo(o, k), Qo(o, ch), s); }
+    gdec[GO::off_Wc(i) + k * CD + ch] += s;
   }
   for (int idx = tid; idx < 5 * 32; idx += nt) {
     const int i = idx / 32, k = idx % 32;
-    double s = 0.0;
-    if (i < 4) { for (int n = 0; n < 32; ++n) s += (double)Wh(i + 1, n, k) * (double)bhat(i + 1, n); }
-    else { for (int o = 0; o < NO; ++o) s += (double)Wo(o, k) * (double)raw[RAW_DBO + o]; }
-    gdec[GO::off_bc(i) + k] += (float)s;
+    float s = 0.f;
+    if (i < 4) { for (int n = 0; n < 32; ++n) s = fmaf(Wh(i + 1, n, k), bhat(i + 1, n), s); }
+    else { for (int o = 0; o < NO; ++o) s = fmaf(Wo(o, k), raw[RAW_DBO + o], s); }
+    gdec[GO::off_bc(i) + k] += s;
     gdec[GO::off_b(i) + k] += bhat(i, k);                                                   // pts_linears.i.bias
   }
   // embedder._B [3][93]
@@ -630,17 +1026,17 @@ __device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const
   // hidden parts of pts_linears.1..4.weight:  S_i + Q_i Wc_{i-1}^T + b^_i bc_{i-1}^T
   for (int idx = tid; idx < 4 * 1024; idx += nt) {
     const int i = 1 + idx / 1024, n = (idx / 32) % 32, k = idx % 32;
-    double s = (double)S(i, n, k) + (double)bhat(i, n) * (double)bc(i - 1, k);
-    for (int ch = 0; ch < CD; ++ch) s += (double)Q(i, n, ch) * (double)Wc(i - 1, k, ch);
+    float s = fmaf(bhat(i, n), bc(i - 1, k), S(i, n, k));
+    for (int ch = 0; ch < CD; ++ch) s = fmaf(Q(i, n, ch), Wc(i - 1, k, ch), s);
     const int K = (i == 3) ? 125 : 32;
-    gdec[GO::off_W(i) + n * K + (i == 3 ? EMB : 0) + k] += (float)s;
+    gdec[GO::off_W(i) + n * K + (i == 3 ? EMB : 0) + k] += s;
   }
   // output_linear.weight [NO_full][32], bias  (NO rows carry gradient; the colour decoder's 4th row gets none)
   for (int idx = tid; idx < NO * 32; idx += nt) {
     const int o = idx / 32, k = idx % 32;
-    double s = (double)raw[RAW_DWOR + o * 32 + k] + (double)raw[RAW_DBO + o] * (double)bc(4, k);
-    for (int ch = 0; ch < CD; ++ch) s += (double)Qo(o, ch) * (double)Wc(4, k, ch);
-    gdec[GO::off_Wo() + o * 32 + k] += (float)s;
+    float s = fmaf(raw[RAW_DBO + o], bc(4, k), raw[RAW_DWOR + o * 32 + k]);
+    for (int ch = 0; ch < CD; ++ch) s = fmaf(Qo(o, ch), Wc(4, k, ch), s);
+    gdec[GO::off_Wo() + o * 32 + k] += s;
   }
   for (int o = tid; o < NO; o += nt) gdec[GO::off_bo() + o] += raw[RAW_DBO + o];
 }
@@ -696,8 +1092,13 @@ int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage) {
 template <int STAGE, bool WG>
 static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStream_t s) {
   const size_t smem = (size_t)((WG ? 16384 + 8192 : 4096) + MlpPackTCB::total()) * 4 + 1024;
-  if (cudaFuncSetAttribute(bwd_tc_kernel<STAGE, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
-  bwd_tc_kernel<STAGE, WG><<<dim3((unsigned)max_ctas, (unsigned)nroles), 128, smem, s>>>(a);
+  if (WG) {
+    if (cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    bwd_tc_wg_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
+  } else {
+    if (cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    bwd_tc_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 128, smem, s>>>(a);
+  }
   ENS_CHECK_CUDA();
   return ENS_OK;
 }
@@ -708,7 +1109,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   const int S = b.ra.S;
   const int64_t P = R * (int64_t)S;
   if (!workspace || workspace_bytes < tc_bwd_workspace_bytes(R, S, stage)) return ENS_ESHAPE;
-  if (wg ? (b.save_r == nullptr) : (b.save_masks == nullptr)) return ENS_EINVAL;
+  if (b.save_masks == nullptr || (wg && b.save_r == nullptr)) return ENS_EINVAL;
   char *base = reinterpret_cast<char *>(workspace);
   double *pts = reinterpret_cast<double *>(base);
   double *z = reinterpret_cast<double *>(base + P * 24);
@@ -758,7 +1159,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     UnfoldArgs u;
     u.raw = raw;
     for (int l = 0; l < 4; ++l) { u.w[l] = b.sc.w[l]; u.gdec[l] = b.gdec[l]; }
-    unfold_kernel<<<ndec, 256, 0, s>>>(u, stage);
+    unfold_kernel<<<dim3(ndec, 24), 256, 0, s>>>(u, stage);
     ENS_CHECK_CUDA();
   }
   if (want_rays) {

@@ -284,6 +284,16 @@ inline int64_t tc_saved_r_bytes(int64_t n_rays, int S, int stage) {
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
   return (int64_t)ndec * ((n_rays * S + 127) / 128) * TC_RSAVE_TILE_FLOATS * (int64_t)sizeof(float);
 }
+// saved kind 3 = [relu outputs | relu mask words]: masks as in kind 2, [decoder][n_tiles32][5][32], n_tiles32 = 4 ceil(P / 128)
+inline int64_t tc_saved3_bytes(int64_t n_rays, int S, int stage, int64_t *r_bytes, int64_t *n_tiles32) {
+  const int64_t rb = tc_saved_r_bytes(n_rays, S, stage);
+  if (rb <= 0) return 0;
+  const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
+  const int64_t nt = 4 * ((n_rays * S + 127) / 128);
+  if (r_bytes) *r_bytes = rb;
+  if (n_tiles32) *n_tiles32 = nt;
+  return rb + (int64_t)ndec * nt * 160 * 4;
+}
 // tcgen05 backward (ens_bwd_tc.cu)
 int tc_render_bwd(BwdArgs &a, int stage, bool wg, void *workspace, int64_t workspace_bytes, cudaStream_t s);
 int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage);

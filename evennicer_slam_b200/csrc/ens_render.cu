@@ -951,10 +951,13 @@ extern "C" int ens_render_fwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   if (saved_with_activations == 3) {
     // tcgen05 forward that keeps the relu outputs r_0..r_4 of every decoder: the forward of the tcgen05 backward WITH
     // decoder gradients (mapping).  Anything that prevents this path is an error (no silent change of format).
-    const int64_t need = tc_saved_r_bytes(n_rays, S, stage);
+    int64_t r_bytes = 0, nt32 = 0;
+    const int64_t need = tc_saved3_bytes(n_rays, S, stage, &r_bytes, &nt32);
     if (need <= 0 || saved == nullptr || !use_mma_forward()) return ENS_EUNSUPPORTED;
     if (saved_bytes < need || (reinterpret_cast<uintptr_t>(saved) & 15)) return ENS_ESHAPE;
     a.save_r = reinterpret_cast<float *>(saved);
+    a.save_masks = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(saved) + r_bytes);
+    a.n_tiles = nt32;
     return tc_render_fwd(a, stage, scratch, scratch_bytes, (cudaStream_t)stream);
   }
   if (saved != nullptr) {
@@ -1001,7 +1004,7 @@ extern "C" int64_t ens_fwd_saved_bytes(int64_t n_rays, int n_samples_total, int 
 }
 
 extern "C" int64_t ens_fwd_saved_bytes_kind(int64_t n_rays, int n_samples_total, int stage, int kind) {
-  if (kind == 3) return use_mma_forward() ? tc_saved_r_bytes(n_rays, n_samples_total, stage) : 0;
+  if (kind == 3) return use_mma_forward() ? tc_saved3_bytes(n_rays, n_samples_total, stage, nullptr, nullptr) : 0;
   if (kind < 0 || kind > 3) return 0;
   return ens_fwd_saved_bytes(n_rays, n_samples_total, stage, kind == 1);
 }
@@ -1065,10 +1068,14 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   a.save_masks = nullptr; a.save_h = nullptr; a.n_tiles = 0; a.mask_fmt = 0;
   if (saved_with_activations < 0 || saved_with_activations > 3) return ENS_EINVAL;
   if (saved_with_activations == 3) {          // relu outputs kept by the tcgen05 forward: tcgen05 backward with decoder gradients
-    const int64_t need = tc_saved_r_bytes(n_rays, S, stage);
+    int64_t r_bytes = 0, nt32 = 0;
+    const int64_t need = tc_saved3_bytes(n_rays, S, stage, &r_bytes, &nt32);
     if (need <= 0 || saved == nullptr) return ENS_EUNSUPPORTED;
     if (saved_bytes < need) return ENS_ESHAPE;
     a.save_r = reinterpret_cast<const float *>(saved);
+    a.save_masks = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(saved) + r_bytes);
+    a.n_tiles = nt32;
+    a.mask_fmt = 1;
     return tc_render_bwd(a, stage, wg, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   const bool have_h = saved_with_activations == 1;
