@@ -49,6 +49,7 @@ class EnsGrads(C.Structure):
 _SIGNATURES = {
     "ens_version": (C.c_int, []),
     "ens_strerror": (C.c_char_p, [C.c_int]),
+    "ens_last_error": (C.c_char_p, []),
     "ens_packed_decoder_floats": (C.c_int64, [C.c_int]),
     "ens_decoder_grad_floats": (C.c_int64, [C.c_int]),
     "ens_decoder_num_tensors": (C.c_int, [C.c_int]),
@@ -121,6 +122,8 @@ def lib():
 def check(rc: int, what: str = ""):
     if rc != ENS_OK:
         msg = lib().ens_strerror(rc).decode()
+        if rc == -3:
+            msg += ": " + lib().ens_last_error().decode()
         raise RuntimeError(f"libens_render: {what} failed: {msg} (code {rc})")
 
 

@@ -29,6 +29,7 @@
 // Roles: the fine decoder's feature vector is 64 wide ([fine | middle], decoder.py:182-187); its middle half needs five
 // more accumulators than a CTA's TMEM holds, so a fourth role (FINE_CM) repeats the fine decoder's hidden chain (Wh only)
 // and accumulates  Q_i[:, 32:64].
+#include <cstdlib>
 #include "ens_tc.cuh"
 
 namespace ens {
@@ -56,6 +57,7 @@ struct BwdTcArgs {
   float *raw_acc;           // [4 roles][RAW_FLOATS]
   float *gp;                // [3 planes][P][3], or null
   int ctas[4];              // persistent CTAs per role
+  long long *dbg;           // optional timestamps (tools/time_passes.py)
 };
 
 // TMEM columns
@@ -307,8 +309,8 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
       if (warp == 0) {
         tc_fence_after();
         if (i >= 1) {
-          issue_gemm<32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_WhT(1) + (i - 1) * 1024, PB::TOT(), 0u);
-          if (TAIL) issue_gemm<32, 32>(tb0 + TB_DC, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_MT(0) + (i - 1) * 1024, PB::TOT(), i == 4 ? 0u : 1u);
+          issue_gemm<32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_WhT(i), PB::TOT(), 0u);
+          if (TAIL) issue_gemm<32, 32>(tb0 + TB_DC, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_MT(i - 1), PB::TOT(), i == 4 ? 0u : 1u);
         }
         if (TAIL && (i == 3 || i == 0))
           issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, i == 3 ? PB::off_W3eT() : PB::off_W0T(), PB::TOT(), i == 3 ? 0u : 1u);
@@ -438,7 +440,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
         }
       }
       if (want_rays && valid) {
-        float *dst = a.gp + ((int64_t)DEC * a.P + pt) * 3;
+        float *dst = a.gp + ((int64_t)DEC * a.P + pt) * 3;          // pose-only form: one plane per decoder
         dst[0] = (float)gp[0]; dst[1] = (float)gp[1]; dst[2] = (float)gp[2];
       }
     }
@@ -492,13 +494,55 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
 //   passes (accumulator = pass):  0 L4 [r3|c]  1 L3 [r2|c]  2 L3 [e0|e1]  3 L3 [e2|c]  4 L2 [r1|c]  5 L1 [r0|c]  6 L0 [e0|c]  7 L0 [e1|e2]
 //   FINE_CM: five passes 0..4 = blocks 4..0, slot B = the middle-level features, slot A unused.
 // =============================================================================================================
-__device__ __forceinline__ void cta_sync256() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void load_row32(const float *__restrict__ src, float (&v)[32]) {
   const float4 *s4 = reinterpret_cast<const float4 *>(src);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { const float4 x = __ldg(s4 + q); v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
+  // streaming load (evict-first): the saved relu outputs are read exactly once and must not push the grids out of L2
+  for (int q = 0; q < 8; ++q) { const float4 x = __ldcs(s4 + q); v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
 }
+
+// tcgen05.st of 32 zero columns
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+               "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n"
+               :: "r"(taddr), "r"(z) : "memory");
+}
+
+// weight-gradient pass, issued by ONE thread in a rolled loop (small code: the issuing warp shares its instruction cache
+// with the staging code)
+__device__ __forceinline__ void issue_wgrad_loop(uint32_t acc, uint32_t sA, uint32_t sB) {
+  constexpr uint32_t IDESC = tc_idesc_mn(128, 32);
+  const uint64_t da = umma_desc_mn(sA, 16384u), dbh = umma_desc_mn(sB, 16384u), dbl = umma_desc_mn(sB + 16384u, 16384u);
+#pragma unroll 4
+  for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbl + (uint64_t)(64 * ks), IDESC, 1u);
+#pragma unroll 4
+  for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
+}
+
+// the k-step `ks` (8 of the K columns) of  D += A[128 x K] * W[N x K]^T  in 3xTF32 -- see issue_gemm
+template <int KMAT, int N>
+__device__ __forceinline__ void issue_gemm_k(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t sw_base, int w_off, int tot, int ks) {
+  const uint64_t dh = umma_desc(sw_base + (uint32_t)w_off * 4u, (KMAT / 4) * 128u) + (uint64_t)(16 * ks);
+  const uint64_t dl = umma_desc(sw_base + (uint32_t)(w_off + tot) * 4u, (KMAT / 4) * 128u) + (uint64_t)(16 * ks);
+  constexpr uint32_t IDESC = tc_idesc(N);
+  umma_ts(d, a_lo + 8 * ks, dh, IDESC, 1u);
+  umma_ts(d, a_hi + 8 * ks, dl, IDESC, 1u);
+  umma_ts(d, a_hi + 8 * ks, dh, IDESC, 1u);
+}
+// a quarter of a weight-gradient pass: points 8 (part + 4 j), j = 0..3, remainder then value of g
+__device__ __forceinline__ void issue_wgrad_part(uint32_t acc, uint32_t sA, uint32_t sB, int part) {
+  constexpr uint32_t IDESC = tc_idesc_mn(128, 32);
+  const uint64_t da = umma_desc_mn(sA, 16384u) + (uint64_t)(64 * part);
+  const uint64_t dbh = umma_desc_mn(sB, 16384u) + (uint64_t)(64 * part), dbl = umma_desc_mn(sB + 16384u, 16384u) + (uint64_t)(64 * part);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) umma_ss(acc, da + (uint64_t)(256 * j), dbl + (uint64_t)(256 * j), IDESC, 1u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) umma_ss(acc, da + (uint64_t)(256 * j), dbh + (uint64_t)(256 * j), IDESC, 1u);
+}
+
+__device__ __forceinline__ void cta_sync288() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
 
 template <int ROLE>
 __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_raw) {
@@ -519,17 +563,16 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
   __shared__ uint32_t tmem_base_s;
   __shared__ float4 sP[128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool isE = warp < 4;
+  const bool isE = warp < 4, isI = warp == 8;       // E: TMEM lanes; H (4..7): M-side; I (8): issues every MMA
   const int pl = tid & 127;          // point of the tile this thread works on
   const int w4 = warp & 3;
 
   {
     const float *gw = a.sc.w[LEVEL] + off_tcb<CD>();
     const uint32_t s0 = smem_u32(sw);
-    for (int i = tid; i < PB::total() / 4; i += 256)
+    for (int i = tid; i < PB::total() / 4; i += 288)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&barD)));
@@ -540,6 +583,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -548,23 +592,11 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
   const uint32_t tb = tb0 + ((uint32_t)(32 * w4) << 16);
   const uint32_t swb = smem_u32(sw), sMBa = smem_u32(sMB), sNBa = smem_u32(sNB);
   uint32_t pw = 0, pd = 0;           // phase parities of barW / barD as this thread has consumed them
-  bool first = true;                 // no weight-gradient pass has been issued yet
+  bool first = true;                 // this thread has no un-consumed weight-gradient pass behind it
 
-  if (isE) {      // zero the weight-gradient accumulators
-    uint32_t zz[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) zz[k] = 0u;
+  if (isE) {      // every accumulator starts at zero and only ever accumulates: g_h | g_c | g_e and the weight-gradient sums
 #pragma unroll 1
-    for (int c = 0; c < NPASS; ++c) {
-      asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                   "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-                   "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
-                   :: "r"(tb + TB_ACC + 32 * c), "r"(zz[0]), "r"(zz[1]), "r"(zz[2]), "r"(zz[3]), "r"(zz[4]), "r"(zz[5]), "r"(zz[6]), "r"(zz[7]),
-                     "r"(zz[8]), "r"(zz[9]), "r"(zz[10]), "r"(zz[11]), "r"(zz[12]), "r"(zz[13]), "r"(zz[14]), "r"(zz[15]),
-                     "r"(zz[16]), "r"(zz[17]), "r"(zz[18]), "r"(zz[19]), "r"(zz[20]), "r"(zz[21]), "r"(zz[22]), "r"(zz[23]),
-                     "r"(zz[24]), "r"(zz[25]), "r"(zz[26]), "r"(zz[27]), "r"(zz[28]), "r"(zz[29]), "r"(zz[30]), "r"(zz[31])
-                   : "memory");
-    }
+    for (int c = TB_DH; c < TB_ACC + 32 * NPASS; c += 32) tmem_zero32(tb + c);
     tmem_st_done();
   }
   tc_fence_before();
@@ -580,10 +612,13 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
 
   const bool want_rays = TAIL && a.gp != nullptr;
   const int nctas = a.ctas[ROLE];
-  // the layer of a pass (-1: Fourier-chunk pass without data gradients)
+  // the block of a pass (-1: Fourier-chunk pass without data gradients)
   auto pass_layer = [](int p) { return TAIL ? (p == 0 ? 4 : (p == 1 ? 3 : (p == 4 ? 2 : (p == 5 ? 1 : (p == 6 ? 0 : -1))))) : 4 - p; };
 
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tile == (int64_t)nctas && (tid == 0 || tid == 128);
+#define ENS_DBG(ps, slot) do { if (dbg_on) a.dbg[((ROLE * 10 + (ps)) * 2 + (tid >> 7)) * 8 + (slot)] = clock64(); } while (0)
+    ENS_DBG(8, 0);
     const int64_t pt = tile * 128 + pl;
     const bool valid = pt < a.P;
     double p[3] = {0.0, 0.0, 0.0};
@@ -602,7 +637,32 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
     else go[0] = g4.w;
     const float *rbase = a.save_r + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
 
-    if (isE) {
+    if (isI) {
+      // ================================ issuer warp ================================
+      // issuing an MMA blocks while the tensor pipe's queue is full, i.e. for about as long as the pass runs: nothing else
+      // may sit behind it, so this warp does nothing but issue.  All GEMMs accumulate (their readers zero the accumulators).
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int i = pass_layer(ps);
+        tc_fence_before();
+        cta_sync288();
+        tc_fence_after();
+        if (i >= 1) {
+          // [g_h | g_c | g_e] += g_u [WhT_i ; MT_{i-1} ; W3eT]
+          if (!TAIL) issue_gemm<32, 32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(i), PB::TOT(), 1u);
+          else if (i == 3) issue_gemm<32, 32, 160>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(3), PB::TOT(), 1u);
+          else issue_gemm<32, 32, 64>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(i), PB::TOT(), 1u);
+          umma_commit(&barD);
+        } else if (i == 0 && TAIL) {
+          issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(0), PB::TOT(), 1u);
+          umma_commit(&barD);
+        }
+        issue_wgrad_loop(tb0 + TB_ACC + 32 * ps, sMBa, sNBa);
+        umma_commit(&barW);
+        __syncwarp();
+      }
+      first = false;
+    } else if (isE) {
       // ================================ E warps ================================
       const Vox vox = make_vox(pn, a.sc.dims[LEVEL]);
       uint32_t mw[5];
@@ -621,115 +681,93 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         }
       }
 #pragma unroll 1
+      ENS_DBG(8, 1);
       for (int ps = 0; ps < NPASS; ++ps) {
         const int i = pass_layer(ps);
+        ENS_DBG(ps, 0);
         if (i >= 0) {
           uint32_t m = 0u;
 #pragma unroll
           for (int k = 0; k < 5; ++k) if (k == i) m = mw[k];
-          float gu[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) gu[k] = ((m >> k) & 1u) ? g[k] : 0.f;
-          const float bs = warp_colsum32(gu);
+          for (int k = 0; k < 32; ++k) g[k] = ((m >> k) & 1u) ? g[k] : 0.f;          // g_u_i
+          const float bs = warp_colsum32(g);
 #pragma unroll
           for (int k = 0; k < 5; ++k) if (k == i) bhat[k] += bs;
+          if (i >= 1 || TAIL) tmem_st32_split(tb + TB_XH, tb + TB_XL, g);           // A operand of the data-gradient GEMM
+          ENS_DBG(ps, 1);
           if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
-          stage_row(sNB, sNB + 4096, pl, gu);
-          if (i >= 1 || TAIL) tmem_st32_split(tb + TB_XH, tb + TB_XL, gu);
+          ENS_DBG(ps, 2);
+          stage_row(sNB, sNB + 4096, pl, g);
           tmem_st_done();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          ENS_DBG(ps, 3);
         } else {
           if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
         }
         first = false;
         tc_fence_before();
-        cta_sync256();
+        cta_sync288();
+        ENS_DBG(ps, 4);
         if (i >= 1) {
           mbar_wait(&barD, pd); pd ^= 1;
           tc_fence_after();
+          ENS_DBG(ps, 5);
           tmem_ld32(tb + TB_DH, g);
+          tmem_zero32(tb + TB_DH);                    // the next block's GEMM accumulates into zero
         } else if (i == 0 && TAIL) {
           mbar_wait(&barD, pd); pd ^= 1;              // g_e complete
           tc_fence_after();
         }
+        ENS_DBG(ps, 6);
       }
+      ENS_DBG(8, 2);
       // ---- tail: feature gradient -> grid scatter + coordinate gradient; embedding gradient ----
       if (TAIL) {
         mbar_wait(&barW, pw); pw ^= 1;                // last pass done: the N-side block doubles as this warp's 32x32 tile
-        first = true;                                 // ... and that wait already consumed the phase the next tile would wait for
+        first = true;                                 // ... and that phase is consumed
         tc_fence_after();
+        ENS_DBG(9, 0);
         float *stile = sNB + w4 * 1024;
-        sP[pl] = make_float4(p32[0], p32[1], p32[2], 0.f);
         double gp[3] = {0.0, 0.0, 0.0};
         float *ggrid = a.ggrid[LEVEL];
-        if (ggrid != nullptr || want_rays) {
+        {
           float gc[32];
           tmem_ld32(tb + TB_DC, gc);
-          const float *MoF = sw + PB::off_MoF();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            float s = gc[k];
-#pragma unroll
-            for (int o = 0; o < NO; ++o) s = fmaf(MoF[o * 32 + k], go[o], s);
-            gc[k] = s;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
-          __syncwarp();
-          float gpn[3];
-          gather_bwd_warp<32>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], vox, valid, stile, want_rays, gpn);
-          if (want_rays) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) gp[k] += __ddiv_rn((double)gpn[k] * 2.0, __dsub_rn(a.sc.hi[k], a.sc.lo[k]));
-          }
-          __syncwarp();
-        }
-        {
-          const float *B = sw + PB::off_B();
-          float gpe[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int jc = 0; jc < 3; ++jc) {
-            float ge[32];
-            tmem_ld32(tb + TB_DE + 32 * jc, ge);
+          tmem_zero32(tb + TB_DC);
+          if (ggrid != nullptr || want_rays) {
+            const float *MoF = sw + PB::off_MoF();
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              const float bx = B[32 * jc + k], by = B[EMBP + 32 * jc + k], bz = B[2 * EMBP + 32 * jc + k];
-              float sq, cq;
-              fast_sincos(fmaf(p32[2], bz, fmaf(p32[1], by, p32[0] * bx)), sq, cq);
-              const float gq = ge[k] * cq;
-              ge[k] = gq;
-              gpe[0] = fmaf(bx, gq, gpe[0]); gpe[1] = fmaf(by, gq, gpe[1]); gpe[2] = fmaf(bz, gq, gpe[2]);
+              float s = gc[k];
+#pragma unroll
+              for (int o = 0; o < NO; ++o) s = fmaf(MoF[o * 32 + k], go[o], s);
+              gc[k] = s;
             }
-            // dB[r][32 jc + k] = sum_pt p[pt][r] g_q[pt][k]: transpose through the warp's tile, lane k walks its column
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
+              *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(gc[4 * q], gc[4 * q + 1], gc[4 * q + 2], gc[4 * q + 3]);
             __syncwarp();
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float v = stile[r * 32 + (lane ^ ((r & 3) << 3))];
-              const float4 pr = sP[32 * w4 + r];
-              s0 = fmaf(pr.x, v, s0); s1 = fmaf(pr.y, v, s1); s2 = fmaf(pr.z, v, s2);
+            ENS_DBG(9, 1);
+            float gpn[3];
+            gather_bwd_warp<32>(a.sc.grid[LEVEL], ggrid, a.sc.dims[LEVEL], vox, valid, stile, want_rays, gpn);
+            ENS_DBG(9, 2);
+            if (want_rays) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) gp[k] += __ddiv_rn((double)gpn[k] * 2.0, __dsub_rn(a.sc.hi[k], a.sc.lo[k]));
             }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) if (q == jc) { dBacc[q][0] += s0; dBacc[q][1] += s1; dBacc[q][2] += s2; }
             __syncwarp();
-          }
-          if (want_rays) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) gp[k] += (double)gpe[k];
           }
         }
-        if (want_rays && valid) {
-          float *dst = a.gp + ((int64_t)DEC * a.P + pt) * 3;
+        if (want_rays && valid) {                     // plane 2 DEC: the trilinear share of d L / d p (H adds the Fourier share)
+          float *dst = a.gp + ((int64_t)(2 * DEC) * a.P + pt) * 3;
           dst[0] = (float)gp[0]; dst[1] = (float)gp[1]; dst[2] = (float)gp[2];
         }
+        tmem_st_done();
         tc_fence_before();
       }
+      ENS_DBG(8, 3);
     } else {
       // ================================ H warps ================================
       float c[32], rn[32];
@@ -778,65 +816,115 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         }
       }
       const float *B = sw + PB::off_B();
-      auto fourier = [&](int jc, float (&e)[32]) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          e[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * jc + k], fmaf(p32[1], B[EMBP + 32 * jc + k], p32[0] * B[32 * jc + k])));
-      };
       bool waited = true;       // the M-side blocks are free (the wait above)
+      ENS_DBG(8, 1);
 #pragma unroll 1
       for (int ps = 0; ps < NPASS; ++ps) {
         const int i = pass_layer(ps);
-        if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }
-        waited = false;
-        first = false;
+        ENS_DBG(ps, 0);
         if (TAIL) {
-          if (i >= 1) stage_row(sMB, sMB + 2 * 4096, pl, rn);                    // slot A = r_{i-1}
-          else if (i == 0) { float e[32]; fourier(0, e); stage_row(sMB, sMB + 2 * 4096, pl, e); }
-          else if (ps == 2) {
-            float e[32];
-            fourier(0, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
-            fourier(1, e); stage_row(sMB + 4096, sMB + 3 * 4096, pl, e);
-          } else if (ps == 3) {
-            float e[32];
-            fourier(2, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
-            stage_row(sMB + 4096, sMB + 3 * 4096, pl, c);                        // the features back into slot B
+          // slot A <- r_{i-1} (blocks 4..1) or a Fourier chunk; slot B <- a Fourier chunk or the features again
+          //   pass:    0   1   2      3      4   5   6    7
+          //   slot A:  r3  r2  e0     e2     r1  r0  e0   e1
+          //   slot B:  .   .   e1     c      .   .   .    e2
+          const int ja = (ps == 2 || ps == 6) ? 0 : (ps == 3 ? 2 : (ps == 7 ? 1 : -1));
+          const int jb = (ps == 2) ? 1 : (ps == 7 ? 2 : -1);
+          float va[32], vb[32];
+          if (ja >= 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              va[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * ja + k], fmaf(p32[1], B[EMBP + 32 * ja + k], p32[0] * B[32 * ja + k])));
           } else {
-            float e[32];
-            fourier(1, e); stage_row(sMB, sMB + 2 * 4096, pl, e);
-            fourier(2, e); stage_row(sMB + 4096, sMB + 3 * 4096, pl, e);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) va[k] = rn[k];
           }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_fence_before();
-        cta_sync256();
-        if (warp == 4) {
-          tc_fence_after();
-          if (i >= 1) {
-            issue_gemm<32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_WhT(1) + (i - 1) * 1024, PB::TOT(), 0u);
-            if (TAIL) issue_gemm<32, 32>(tb0 + TB_DC, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_MT(0) + (i - 1) * 1024, PB::TOT(), i == 4 ? 0u : 1u);
+          if (jb >= 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              vb[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * jb + k], fmaf(p32[1], B[EMBP + 32 * jb + k], p32[0] * B[32 * jb + k])));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) vb[k] = c[k];
           }
-          if (TAIL && (i == 3 || i == 0))
-            issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, i == 3 ? PB::off_W3eT() : PB::off_W0T(), PB::TOT(), i == 3 ? 0u : 1u);
-          if (i >= 1 || (i == 0 && TAIL)) umma_commit(&barD);
-          issue_wgrad(tb0 + TB_ACC + 32 * ps, sMBa, sNBa);
-          umma_commit(&barW);
-          __syncwarp();
-        }
-        // the next main pass's slot A: r_{i-2}, fetched while this pass's MMAs run
-        if (TAIL) {
+          // the next main pass's slot A (r_{i-2}) is fetched while this pass's MMAs run
           const int nxt = (ps + 1 < NPASS) ? pass_layer(ps + 1) : -1;
           if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
+          ENS_DBG(ps, 1);
+          if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }
+          ENS_DBG(ps, 2);
+          stage_row(sMB, sMB + 2 * 4096, pl, va);
+          if (jb >= 0 || ps == 3) stage_row(sMB + 4096, sMB + 3 * 4096, pl, vb);
+          ENS_DBG(ps, 3);
+        } else {
+          if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }
         }
+        waited = false;
+        first = false;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        cta_sync288();
+        ENS_DBG(ps, 4);
+        ENS_DBG(ps, 5);
+      }
+      if (TAIL) {
+        // ---- Fourier backward (the E warps do the trilinear backward meanwhile): g_q = g_e cos(p B), d L / d p += B g_q, dB ----
+        mbar_wait(&barW, pw); pw ^= 1;                // last pass done (so is every data-gradient GEMM issued before it):
+        first = true;                                 // slot B doubles as this warp's 32x32 tile; that phase is consumed
+        tc_fence_after();
+        ENS_DBG(9, 0);
+        float *stile = sMB + 4096 + w4 * 1024;
+        sP[pl] = make_float4(p32[0], p32[1], p32[2], 0.f);
+        {
+          float gpe[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int jc = 0; jc < 3; ++jc) {
+            float ge[32];
+            tmem_ld32(tb + TB_DE + 32 * jc, ge);
+            tmem_zero32(tb + TB_DE + 32 * jc);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float bx = B[32 * jc + k], by = B[EMBP + 32 * jc + k], bz = B[2 * EMBP + 32 * jc + k];
+              float sq, cq;
+              fast_sincos(fmaf(p32[2], bz, fmaf(p32[1], by, p32[0] * bx)), sq, cq);
+              const float gq = ge[k] * cq;
+              ge[k] = gq;
+              gpe[0] = fmaf(bx, gq, gpe[0]); gpe[1] = fmaf(by, gq, gpe[1]); gpe[2] = fmaf(bz, gq, gpe[2]);
+            }
+            // dB[r][32 jc + k] = sum_pt p[pt][r] g_q[pt][k]: transpose through the warp's tile, lane k walks its column
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4 *>(stile + lane * 32 + ((4 * q) ^ ((lane & 3) << 3))) = make_float4(ge[4 * q], ge[4 * q + 1], ge[4 * q + 2], ge[4 * q + 3]);
+            __syncwarp();
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float v = stile[r * 32 + (lane ^ ((r & 3) << 3))];
+              const float4 pr = sP[32 * w4 + r];
+              s0 = fmaf(pr.x, v, s0); s1 = fmaf(pr.y, v, s1); s2 = fmaf(pr.z, v, s2);
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) if (q == jc) { dBacc[q][0] += s0; dBacc[q][1] += s1; dBacc[q][2] += s2; }
+            __syncwarp();
+          }
+          if (want_rays && valid) {                   // plane 2 DEC + 1
+            float *dst = a.gp + ((int64_t)(2 * DEC + 1) * a.P + pt) * 3;
+            dst[0] = gpe[0]; dst[1] = gpe[1]; dst[2] = gpe[2];
+          }
+        }
+        tmem_st_done();
+        ENS_DBG(9, 1);
       }
     }
+#undef ENS_DBG
   }
 
   // ---- flush the CTA's sums ----
-  if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+  if (!first && !isI) { mbar_wait(&barW, pw); pw ^= 1; }
   tc_fence_after();
   float *raw = a.raw_acc + (int64_t)ROLE * RAW_FLOATS;
-  if (isE) {
+  if (isI) {
+  } else if (isE) {
 #pragma unroll 1
     for (int acc = 0; acc < NPASS; ++acc) {
       float v[32];
@@ -847,13 +935,13 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
     }
 #pragma unroll
     for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
+  } else {
     if (TAIL) {
 #pragma unroll
       for (int jc = 0; jc < 3; ++jc)
 #pragma unroll
         for (int r = 0; r < 3; ++r) atomicAdd(raw + RAW_DB + r * 96 + 32 * jc + lane, dBacc[jc][r]);
     }
-  } else {
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
       atomicAdd(raw + RAW_DWOR + o * 32 + lane, dwor[o]);
@@ -867,7 +955,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(256, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
+__global__ void __launch_bounds__(288, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
   const int role = blockIdx.y;
   if ((int)blockIdx.x >= a.ctas[role]) return;
@@ -952,24 +1040,38 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(DevScene sc, const f
   }
 }
 
-// g_rays_o = sum_s g_p, g_rays_d = sum_s z_s g_p over the role planes (float64 sums, as the fused kernels)
+// g_rays_o = sum_s g_p, g_rays_d = sum_s z_s g_p over the role planes (float64 sums, as the fused kernels); a warp per ray
 __global__ void __launch_bounds__(128) rays_reduce_kernel(const float *__restrict__ gp, int n_planes, const double *__restrict__ z,
                                                           int64_t R, int S, float *__restrict__ g_rays_o, float *__restrict__ g_rays_d) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t ray = t / 3;
-  const int s = (int)(t % 3);
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (ray >= R) return;
   const int64_t P = R * (int64_t)S;
-  double so = 0.0, sd = 0.0;
-  for (int k = 0; k < S; ++k) {
+  double so[3] = {0.0, 0.0, 0.0}, sd[3] = {0.0, 0.0, 0.0};
+  for (int k = lane; k < S; k += 32) {
     const int64_t pi = ray * S + k;
-    double gk = 0.0;
-    for (int q = 0; q < n_planes; ++q) gk += (double)gp[((int64_t)q * P + pi) * 3 + s];
-    so += gk;
-    sd += gk * z[pi];
+    const double zk = z[pi];
+    double gk[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < n_planes; ++q) {
+      const float *src = gp + ((int64_t)q * P + pi) * 3;
+      gk[0] += (double)src[0]; gk[1] += (double)src[1]; gk[2] += (double)src[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { so[c] += gk[c]; sd[c] += gk[c] * zk; }
   }
-  if (g_rays_o) g_rays_o[ray * 3 + s] = (float)so;
-  if (g_rays_d) g_rays_d[ray * 3 + s] = (float)sd;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      so[c] += __shfl_xor_sync(0xffffffffu, so[c], off);
+      sd[c] += __shfl_xor_sync(0xffffffffu, sd[c], off);
+    }
+  if (lane < 3) {
+    const double vo = lane == 0 ? so[0] : (lane == 1 ? so[1] : so[2]);
+    const double vd = lane == 0 ? sd[0] : (lane == 1 ? sd[1] : sd[2]);
+    if (g_rays_o) g_rays_o[ray * 3 + lane] = (float)vo;
+    if (g_rays_d) g_rays_d[ray * 3 + lane] = (float)vd;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -977,11 +1079,29 @@ __global__ void __launch_bounds__(128) rays_reduce_kernel(const float *__restric
 // blob: the decoder's packed weights (fma section MlpPack<CD>: W_iT [K_i][32], b_i, Wc_iT [CD][32], bc_i, WoT [32][4], bo).
 // ---------------------------------------------------------------------------------------------
 // NO = output rows that carry gradient, NOF = rows of output_linear (the colour decoder's 4th row gets none, decoder.py:341)
+// Every CTA stages what the decoder's unfolding reads -- the raw sums (69 KB; FINE_CM's too for the fine decoder) and the fma
+// section of the packed weights -- in shared memory (coalesced), then its threads take output elements round-robin.
 template <int CD, int NO, int NOF>
-__device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const float *__restrict__ raw_cm,
-                                            const float *__restrict__ blob, float *__restrict__ gdec) {
+__device__ __forceinline__ void unfold_body(const float *__restrict__ graw, const float *__restrict__ graw_cm,
+                                            const float *__restrict__ gblob, float *__restrict__ gdec, float *__restrict__ smem) {
   using PK = MlpPack<CD>;
   using GO = MlpGrad<CD, NOF>;
+  float *raw = smem, *raw_cm = smem + RAW_FLOATS, *blob = raw_cm + (CD == 64 ? RAW_FLOATS : 0);
+  {
+    // cp.async: every 16-byte copy of the CTA in flight at once
+    auto copy16 = [&](float *dst, const float *src, int n4) {
+      const uint32_t s0 = smem_u32(dst);
+      for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(src + i * 4) : "memory");
+    };
+    copy16(raw, graw, RAW_FLOATS / 4);
+    if (CD == 64) copy16(raw_cm, graw_cm, RAW_FLOATS / 4);
+    static_assert(PK::total() % 4 == 0, "blob section must be a whole number of 16-byte copies");
+    copy16(blob, gblob, PK::total() / 4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
   const int tid = blockIdx.y * blockDim.x + threadIdx.x, nt = gridDim.y * blockDim.x;
   auto accS = [](int i) { return i == 4 ? 0 : (i == 3 ? 1 : (i == 2 ? 4 : 5)); };                  // i = 1..4
   auto S = [&](int i, int n, int k) { return raw[accS(i) * 2048 + k * 32 + n]; };
@@ -1001,7 +1121,9 @@ __device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const
   for (int idx = tid; idx < 5 * 32 * CD; idx += nt) {
     const int i = idx / (32 * CD), k = (idx / CD) % 32, ch = idx % CD;
     float s = 0.f;
-    if (i < 4) { for (int n = 0; n < 32; ++n) s = fmaf(Wh(i + 1, n, k), Q(i + 1, n, ch), s); }
+    // the lanes of a warp differ in ch = the ROW of the staged sums: start each lane's walk over n at its own column
+    // (bank-conflict free; the order of a 32-term fp32 sum is free)
+    if (i < 4) { for (int q = 0; q < 32; ++q) { const int n = (q + threadIdx.x) & 31; s = fmaf(Wh(i + 1, n, k), Q(i + 1, n, ch), s); } }
     else { for (int o = 0; o < NO; ++o) s = fmaf(Wo(o, k), Qo(o, ch), s); }
     gdec[GO::off_Wc(i) + k * CD + ch] += s;
   }
@@ -1031,7 +1153,7 @@ __device__ __forceinline__ void unfold_body(const float *__restrict__ raw, const
     const int K = (i == 3) ? 125 : 32;
     gdec[GO::off_W(i) + n * K + (i == 3 ? EMB : 0) + k] += s;
   }
-  // output_linear.weight [NO_full][32], bias  (NO rows carry gradient; the colour decoder's 4th row gets none)
+  // output_linear.weight [NOF][32], bias  (NO rows carry gradient)
   for (int idx = tid; idx < NO * 32; idx += nt) {
     const int o = idx / 32, k = idx % 32;
     float s = fmaf(raw[RAW_DBO + o], bc(4, k), raw[RAW_DWOR + o * 32 + k]);
@@ -1047,14 +1169,17 @@ struct UnfoldArgs {
   float *gdec[4];
 };
 
-__global__ void __launch_bounds__(256) unfold_kernel(UnfoldArgs a, int stage) {
+constexpr int UNFOLD_SMEM_FLOATS = 2 * RAW_FLOATS + MlpPack<64>::total();
+
+__global__ void __launch_bounds__(512) unfold_kernel(UnfoldArgs a, int stage) {
+  extern __shared__ __align__(16) float usm[];
   const int d = blockIdx.x;
-  if (d == 0) unfold_body<32, 1, 1>(a.raw + ROLE_MIDDLE * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_MIDDLE], a.gdec[ENS_LEVEL_MIDDLE]);
+  if (d == 0) unfold_body<32, 1, 1>(a.raw + ROLE_MIDDLE * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_MIDDLE], a.gdec[ENS_LEVEL_MIDDLE], usm);
   else if (d == 1) {
     if (stage >= ENS_STAGE_FINE)
-      unfold_body<64, 1, 1>(a.raw + ROLE_FINE * RAW_FLOATS, a.raw + ROLE_FINE_CM * RAW_FLOATS, a.w[ENS_LEVEL_FINE], a.gdec[ENS_LEVEL_FINE]);
+      unfold_body<64, 1, 1>(a.raw + ROLE_FINE * RAW_FLOATS, a.raw + ROLE_FINE_CM * RAW_FLOATS, a.w[ENS_LEVEL_FINE], a.gdec[ENS_LEVEL_FINE], usm);
   } else if (stage == ENS_STAGE_COLOR) {
-    unfold_body<32, 3, 4>(a.raw + ROLE_COLOR * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_COLOR], a.gdec[ENS_LEVEL_COLOR]);
+    unfold_body<32, 3, 4>(a.raw + ROLE_COLOR * RAW_FLOATS, nullptr, a.w[ENS_LEVEL_COLOR], a.gdec[ENS_LEVEL_COLOR], usm);
   }
 }
 
@@ -1086,17 +1211,17 @@ __global__ void __launch_bounds__(NT_MMA) place_bwd_kernel(DevScene sc, RayArgs 
 int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage) {
   if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
   const int64_t P = n_rays * (int64_t)S;
-  return P * (24 + 8 + 16 + 36) + 4 * (int64_t)RAW_FLOATS * 4 + 256;
+  return P * (24 + 8 + 16 + 72) + 4 * (int64_t)RAW_FLOATS * 4 + 256;
 }
 
 template <int STAGE, bool WG>
 static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStream_t s) {
   const size_t smem = (size_t)((WG ? 16384 + 8192 : 4096) + MlpPackTCB::total()) * 4 + 1024;
   if (WG) {
-    if (cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
-    bwd_tc_wg_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_tc_wg_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
   } else {
-    if (cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd_tc_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 128, smem, s>>>(a);
   }
   ENS_CHECK_CUDA();
@@ -1115,7 +1240,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   double *z = reinterpret_cast<double *>(base + P * 24);
   float4 *gout = reinterpret_cast<float4 *>(base + P * 32);
   float *gp = reinterpret_cast<float *>(base + P * 48);
-  float *raw = reinterpret_cast<float *>(base + ((P * 84 + 255) / 256) * 256);
+  float *raw = reinterpret_cast<float *>(base + ((P * 120 + 255) / 256) * 256);
   const bool want_rays = b.g_rays_o != nullptr || b.g_rays_d != nullptr;
 
   b.ra.rpc = NT_MMA / S;
@@ -1124,19 +1249,24 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   composite_bwd_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(b.sc, reinterpret_cast<const float4 *>(b.raw), z, pts, R, S,
                                                               b.g_depth, b.g_var, b.g_color, gout);
   ENS_CHECK_CUDA();
-  if (wg && cudaMemsetAsync(raw, 0, 4 * (size_t)RAW_FLOATS * 4, s) != cudaSuccess) return ENS_ECUDA;
+  if (wg) ENS_CUDA_CALL(cudaMemsetAsync(raw, 0, 4 * (size_t)RAW_FLOATS * 4, s));
 
   BwdTcArgs a;
   a.sc = b.sc; a.pts = pts; a.gout = gout; a.P = P; a.n_tiles = (P + 127) / 128;
   a.save_r = b.save_r; a.save_m = b.save_masks; a.m_stride = b.n_tiles * 160;
   for (int l = 0; l < 4; ++l) a.ggrid[l] = b.ggrid[l];
   a.raw_acc = raw; a.gp = want_rays ? gp : nullptr;
+  {
+    const char *v = std::getenv("ENS_BWD_TC_DBG");          // tools/time_passes.py: device address of a long long[640]
+    a.dbg = v ? reinterpret_cast<long long *>(std::strtoull(v, nullptr, 0)) : nullptr;
+  }
   int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaGetDevice(&dev));
+  ENS_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // persistent CTAs per role, in proportion to the work of a tile (the FINE_CM role runs the hidden chain only)
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
   const int nroles = (wg && ndec > 1) ? 4 : ndec;
-  const double cost[4] = {1.0, 1.0, 1.0, 0.45};
+  const double cost[4] = {1.0, 1.0, 1.0, 0.36};
   double tot = 0.0;
   for (int r = 0; r < 4; ++r) { a.ctas[r] = 0; if (r < ndec || (r == 3 && nroles == 4)) tot += cost[r]; }
   int max_ctas = 0;
@@ -1159,11 +1289,12 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     UnfoldArgs u;
     u.raw = raw;
     for (int l = 0; l < 4; ++l) { u.w[l] = b.sc.w[l]; u.gdec[l] = b.gdec[l]; }
-    unfold_kernel<<<dim3(ndec, 24), 256, 0, s>>>(u, stage);
+    ENS_CUDA_CALL(cudaFuncSetAttribute(unfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UNFOLD_SMEM_FLOATS * 4));
+    unfold_kernel<<<dim3(ndec, 6), 512, UNFOLD_SMEM_FLOATS * 4, s>>>(u, stage);
     ENS_CHECK_CUDA();
   }
   if (want_rays) {
-    rays_reduce_kernel<<<(unsigned)((R * 3 + 127) / 128), 128, 0, s>>>(gp, ndec, z, R, S, b.g_rays_o, b.g_rays_d);
+    rays_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(gp, wg ? 2 * ndec : ndec, z, R, S, b.g_rays_o, b.g_rays_d);
     ENS_CHECK_CUDA();
   }
   return ENS_OK;

@@ -1,5 +1,15 @@
 // Version / error strings / size queries of the C ABI (include/ens_render.h).
+#include <cstdio>
 #include "ens_common.cuh"
+
+namespace ens {
+static thread_local char g_last_error[256] = "";
+void note_cuda_error(cudaError_t e, const char *file, int line) {
+  std::snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s:%d)", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
+}
+}  // namespace ens
+
+extern "C" const char *ens_last_error(void) { return ens::g_last_error; }
 
 extern "C" int ens_version(void) { return ENS_ABI_VERSION; }
 
@@ -8,7 +18,7 @@ extern "C" const char *ens_strerror(int code) {
     case ENS_OK: return "ok";
     case ENS_EINVAL: return "invalid argument (null pointer, bad enum or negative size)";
     case ENS_ESHAPE: return "inconsistent shape or size";
-    case ENS_ECUDA: return "CUDA error (see cudaGetLastError)";
+    case ENS_ECUDA: return "CUDA error (ens_last_error() has the runtime's message)";
     case ENS_ENCCL: return "collective error";
     case ENS_EUNSUPPORTED: return "unsupported rendering mode (N_importance>0, occupancy=False, perturb>0 or lindisp)";
     default: return "unknown error";

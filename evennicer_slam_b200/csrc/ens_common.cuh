@@ -5,10 +5,19 @@
 
 #include "../../include/ens_render.h"
 
+// Launch check: cudaGetLastError CLEARS a non-sticky error (bad launch configuration, too much shared memory), so a failed
+// launch does not poison every later call of this library or of PyTorch; the message is kept for ens_last_error().
+namespace ens { void note_cuda_error(cudaError_t e, const char *file, int line); }
 #define ENS_CHECK_CUDA()                                   \
   do {                                                     \
-    cudaError_t e__ = cudaPeekAtLastError();               \
-    if (e__ != cudaSuccess) return ENS_ECUDA;              \
+    cudaError_t e__ = cudaGetLastError();                  \
+    if (e__ != cudaSuccess) { ens::note_cuda_error(e__, __FILE__, __LINE__); return ENS_ECUDA; } \
+  } while (0)
+
+#define ENS_CUDA_CALL(x)                                  \
+  do {                                                     \
+    cudaError_t e__ = (x);                                 \
+    if (e__ != cudaSuccess) { (void)cudaGetLastError(); ens::note_cuda_error(e__, __FILE__, __LINE__); return ENS_ECUDA; } \
   } while (0)
 
 namespace ens {
@@ -193,10 +202,13 @@ __host__ __device__ constexpr int canon_off(int n, int k, int K) { return (n / 8
 //   then: B [3][96], Wo [4][32] (rows >= NO zero), MoF [4][32] = Mo[:, :32]
 // ---------------------------------------------------------------------------------------------
 struct MlpPackTCB {
-  __host__ __device__ static constexpr int off_WhT(int i) { return (i - 1) * 1024; }             // i = 1..4
-  __host__ __device__ static constexpr int off_MT(int i) { return 4096 + i * 1024; }             // i = 0..3
-  __host__ __device__ static constexpr int off_W0T() { return 8192; }
-  __host__ __device__ static constexpr int off_W3eT() { return 8192 + 32 * EMBP; }
+  // the matrices one block's data-gradient GEMM reads are CONTIGUOUS, so  [g_h | g_c | g_e] (adjacent TMEM columns) is ONE
+  // accumulating GEMM per block:   L4 [WhT_4; MT_3]   L3 [WhT_3; MT_2; W3eT]   L2 [WhT_2; MT_1]   L1 [WhT_1; MT_0]   L0 [W0T]
+  __host__ __device__ static constexpr int off_G(int i) { return i == 4 ? 0 : (i == 3 ? 2048 : (i == 2 ? 7168 : (i == 1 ? 9216 : 11264))); }
+  __host__ __device__ static constexpr int off_WhT(int i) { return off_G(i); }                   // i = 1..4
+  __host__ __device__ static constexpr int off_MT(int i) { return off_G(i + 1) + 1024; }         // i = 0..3
+  __host__ __device__ static constexpr int off_W3eT() { return off_G(3) + 2048; }
+  __host__ __device__ static constexpr int off_W0T() { return off_G(0); }
   __host__ __device__ static constexpr int TOT() { return 8192 + 2 * 32 * EMBP; }
   __host__ __device__ static constexpr int off_B() { return 2 * TOT(); }
   __host__ __device__ static constexpr int off_Wo() { return off_B() + 3 * EMBP; }

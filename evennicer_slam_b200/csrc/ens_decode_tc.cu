@@ -168,7 +168,8 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
       if (a.rsave != nullptr) {                   // saved for the backward with decoder gradients (every lane: padded tile)
         float4 *dst = reinterpret_cast<float4 *>(a.rsave + ((tile * 5 + i) * 128 + gt) * 32);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = valid ? make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 8; ++q)              // streaming store: read once by the backward, keep the grids in L2
+          __stcs(dst + q, valid ? make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f));
       }
       if (i < 4) {
         tmem_st32_split(tb + TC_XH, tb + TC_XL, r);
@@ -275,10 +276,10 @@ static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_
   const int64_t pairs = ((n + 127) / 128 + 1) / 2;
   const unsigned g = (unsigned)(pairs < sms ? pairs : sms);
   if (f64) {
-    if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     decode_tc_kernel<LEVEL, CD, NO, true><<<g, 256, smem, s>>>(a);
   } else {
-    if (cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(decode_tc_kernel<LEVEL, CD, NO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     decode_tc_kernel<LEVEL, CD, NO, false><<<g, 256, smem, s>>>(a);
   }
   ENS_CHECK_CUDA();
@@ -459,7 +460,7 @@ static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P
     m.rsave[d] = a.save_r ? a.save_r + (int64_t)d * rstride : nullptr;
   }
   const size_t smem = (size_t)(MlpPackTC<64>::total() + 8 * 1024) * 4;       // the fine decoder's blob is the largest
-  if (cudaFuncSetAttribute(decode_tc_multi_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaFuncSetAttribute(decode_tc_multi_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t pairs = ((P + 127) / 128 + 1) / 2;
   decode_tc_multi_kernel<STAGE><<<dim3((unsigned)pairs, ndec), 256, smem, s>>>(m);
   ENS_CHECK_CUDA();

@@ -165,7 +165,7 @@ extern "C" int ens_event_loss(const float *gt, const float *pred, int H, int W, 
     off += ks;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (cudaMemsetAsync(loss_parts, 0, sizeof(double) * (2 + n_kernels), st) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaMemsetAsync(loss_parts, 0, sizeof(double) * (2 + n_kernels), st));
   if (H == 0 || W == 0 || C == 0) return ENS_OK;
   dim3 grid((W + EV_T - 1) / EV_T, (H + EV_T - 1) / EV_T, C);
   event_loss_kernel<<<grid, EV_T * EV_T, 0, st>>>(a);

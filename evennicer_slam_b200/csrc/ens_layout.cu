@@ -232,11 +232,15 @@ __device__ __forceinline__ void pack_mlp_tcb_body(const PtrTable &t, float *__re
   if (idx < 2 * P::TOT()) {
     const bool lo = idx >= P::TOT();
     int o = lo ? idx - P::TOT() : idx;
-    int mat, i = 0;
-    if (o < P::off_MT(0)) { mat = 0; i = 1 + o / 1024; o %= 1024; }
-    else if (o < P::off_W0T()) { mat = 1; o -= P::off_MT(0); i = o / 1024; o %= 1024; }
-    else if (o < P::off_W3eT()) { mat = 2; o -= P::off_W0T(); }
-    else { mat = 3; o -= P::off_W3eT(); }
+    int mat = -1, i = 0;          // mat 0: WhT_i, 1: MT_i, 2: W0T, 3: W3eT
+    if (o >= P::off_W0T()) { mat = 2; o -= P::off_W0T(); }
+    else if (o >= P::off_W3eT() && o < P::off_G(2)) { mat = 3; o -= P::off_W3eT(); }
+    else {
+      for (int q = 1; q <= 4; ++q) {
+        if (o >= P::off_WhT(q) && o < P::off_WhT(q) + 1024) { mat = 0; i = q; o -= P::off_WhT(q); break; }
+        if (o >= P::off_MT(q - 1) && o < P::off_MT(q - 1) + 1024) { mat = 1; i = q - 1; o -= P::off_MT(q - 1); break; }
+      }
+    }
     // canonical [rows][K = 32]: row group of 8 = 256 floats, k group of 4 = 32 floats
     const int ri = o / 256, r1 = o % 256;
     const int ki = r1 / 32, r2 = r1 % 32;

@@ -23,7 +23,9 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) 
 // below the float32 rounding of q itself (ulp(300) = 3e-5).  libdevice sinf() costs ~40 instructions per call
 // and was half of the kernel's issue slots.
 __device__ __forceinline__ float reduce_2pi(float q) {
-  const float k = rintf(q * 0.15915494309189535f);
+  // round-to-nearest by the 1.5 * 2^23 trick (|q / 2 pi| < 2^22): two FMA-pipe adds instead of FRND on the quarter-rate XU pipe,
+  // which the sines already load
+  const float k = __fsub_rn(__fadd_rn(q * 0.15915494309189535f, 12582912.f), 12582912.f);
   float r = fmaf(k, -6.28125f, q);
   r = fmaf(k, -1.9353071693331003e-3f, r);   // float32(2*pi - 6.28125)
   r = fmaf(k, -1.0253131677e-11f, r);        // what the float32 rounding of the previous constant left
@@ -358,8 +360,22 @@ __device__ __forceinline__ void gather_bwd_warp(const float *__restrict__ grid, 
   const int cq = lane & 7, pp = lane >> 3;
   const int sx = C, sy = X * C, sz = X * Y * C;
   float mx = 0.f, my = 0.f, mz = 0.f;
-#pragma unroll 1
+  // the eight corner lines of a point are re-read for the coordinate gradient: with few warps per SM (the tcgen05 kernels)
+  // that L2 latency is exposed once per group, so the lines of the group after next are prefetched into L1 meanwhile
+  auto prefetch_group = [&](int g2) {
+    const int src2 = 4 * g2 + pp;
+    const int b2 = __shfl_sync(0xffffffffu, base, src2);
+    const unsigned ok2 = __shfl_sync(0xffffffffu, okbits, src2);
+    if (cq < 8) {
+      const int c = cq;                                              // lane cq of the point's eight fetches corner cq
+      const int off = b2 + ((c & 1) && (ok2 & 1u) ? sx : 0) + ((c & 2) && (ok2 & 2u) ? sy : 0) + ((c & 4) && (ok2 & 4u) ? sz : 0);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(grid + off));
+    }
+  };
+  if (want_coord) { prefetch_group(0); prefetch_group(1); prefetch_group(2); prefetch_group(3); }
+#pragma unroll 2
   for (int grp = 0; grp < 8; ++grp) {
+    if (want_coord && grp + 4 < 8) prefetch_group(grp + 4);
     const int src = 4 * grp + pp;
     const int b = __shfl_sync(0xffffffffu, base, src);
     const float fx1 = __shfl_sync(0xffffffffu, v.fx, src), fx0 = __shfl_sync(0xffffffffu, v.gx, src);

@@ -843,10 +843,10 @@ static int launch_eval(const DevScene &sc, const void *pts, int f64, int64_t n, 
   const size_t smem = (size_t)(((StageInfo<STAGE>::WMAX + 3) & ~3) + 128 * StageInfo<STAGE>::CP) * 4;
   const unsigned g = (unsigned)((n + 127) / 128);
   if (f64) {
-    if (cudaFuncSetAttribute(eval_points_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(eval_points_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eval_points_kernel<STAGE, true><<<g, 128, smem, s>>>(sc, pts, n, am, out4);
   } else {
-    if (cudaFuncSetAttribute(eval_points_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(eval_points_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eval_points_kernel<STAGE, false><<<g, 128, smem, s>>>(sc, pts, n, am, out4);
   }
   ENS_CHECK_CUDA();
@@ -859,7 +859,7 @@ static int launch_fwd(FwdArgs &a, cudaStream_t s) {
   constexpr int NT = NT_RENDER;
   a.ra.rpc = NT / a.ra.S;
   const size_t smem = fwd_smem_bytes<STAGE, NT>();
-  if (cudaFuncSetAttribute(render_fwd_kernel<STAGE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaFuncSetAttribute(render_fwd_kernel<STAGE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   render_fwd_kernel<STAGE, NT><<<g, NT, smem, s>>>(a);
   ENS_CHECK_CUDA();
@@ -871,7 +871,7 @@ static int launch_bwd(BwdArgs &a, cudaStream_t s) {
   constexpr int NT = NT_RENDER;
   a.ra.rpc = NT / a.ra.S;
   const size_t smem = bwd_smem_bytes<STAGE, NT, WG>();
-  if (cudaFuncSetAttribute(render_bwd_kernel<STAGE, NT, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaFuncSetAttribute(render_bwd_kernel<STAGE, NT, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   render_bwd_kernel<STAGE, NT, WG><<<g, NT, smem, s>>>(a);
   ENS_CHECK_CUDA();

@@ -196,10 +196,10 @@ static int launch_eval_mma(const DevScene &sc, const void *pts, int f64, int64_t
   const size_t smem = (size_t)(MmaStage<STAGE>::WMAX + NT_MMA * MmaStage<STAGE>::RS) * 4;
   const unsigned g = (unsigned)((n + NT_MMA - 1) / NT_MMA);
   if (f64) {
-    if (cudaFuncSetAttribute(eval_points_mma_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(eval_points_mma_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eval_points_mma_kernel<STAGE, true><<<g, NT_MMA, smem, s>>>(sc, pts, n, am, out4);
   } else {
-    if (cudaFuncSetAttribute(eval_points_mma_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+    ENS_CUDA_CALL(cudaFuncSetAttribute(eval_points_mma_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eval_points_mma_kernel<STAGE, false><<<g, NT_MMA, smem, s>>>(sc, pts, n, am, out4);
   }
   ENS_CHECK_CUDA();
@@ -221,7 +221,7 @@ static int launch_fwd_mma(FwdArgs &a, cudaStream_t s) {
   constexpr int NT = NT_MMA;
   a.ra.rpc = NT / a.ra.S;
   const size_t smem = (size_t)(MmaStage<STAGE>::WMAX + NT * MmaStage<STAGE>::RS) * 4 + (size_t)NT * (8 + 8 + 16 + 4 + 4);
-  if (cudaFuncSetAttribute(render_fwd_mma_kernel<STAGE, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaFuncSetAttribute(render_fwd_mma_kernel<STAGE, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   render_fwd_mma_kernel<STAGE, SAVE><<<g, NT, smem, s>>>(a);
   ENS_CHECK_CUDA();

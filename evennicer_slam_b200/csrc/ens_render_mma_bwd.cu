@@ -1031,7 +1031,7 @@ static int launch_bwd_mma_any(BwdArgs &a, bool wg, cudaStream_t s) {
   int rc = launch_bwd_mma<STAGE, false, false, true>(a, s);
   if (rc != ENS_OK) return rc;
   const size_t smem = (size_t)WGRAD_SMEM_FLOATS * 4;
-  if (cudaFuncSetAttribute(wgrad_split_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ENS_ECUDA;
+  ENS_CUDA_CALL(cudaFuncSetAttribute(wgrad_split_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ndec = (STAGE == ENS_STAGE_MIDDLE) ? 1 : (STAGE == ENS_STAGE_FINE ? 2 : 3);
   int64_t ctas = 296 / ndec;
   if (ctas > tiles) ctas = tiles;

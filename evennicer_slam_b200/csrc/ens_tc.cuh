@@ -34,7 +34,10 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE_%=;\n\t"
       "TC_WAIT_%=:\n\t"
+      "nanosleep.u32 40;\n\t"                       // a spinning warp steals issue slots from the warp it shares the scheduler with
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra TC_DONE_%=;\n\t"
       "bra TC_WAIT_%=;\n\t"

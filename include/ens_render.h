@@ -43,7 +43,7 @@ enum {
   ENS_OK = 0,
   ENS_EINVAL = -1,       /* null pointer / bad enum / negative size */
   ENS_ESHAPE = -2,       /* inconsistent sizes */
-  ENS_ECUDA = -3,        /* a CUDA call failed; cudaGetLastError is preserved */
+  ENS_ECUDA = -3,        /* a CUDA call failed; ens_last_error() has the message */
   ENS_ENCCL = -4,        /* reserved (collectives live in torch.distributed) */
   ENS_EUNSUPPORTED = -5  /* iMAP modes: N_importance>0, occupancy=False, perturb>0, lindisp */
 };
@@ -89,6 +89,9 @@ typedef struct EnsGrads {
 
 int ens_version(void);
 const char *ens_strerror(int code);
+/* message of the last CUDA error a call of this thread returned ENS_ECUDA for ("" if none); the error itself has been
+ * cleared from the runtime (cudaGetLastError), so it does not leak into later calls. */
+const char *ens_last_error(void);
 
 /* number of floats in a packed decoder blob / in the flat gradient buffer of a decoder */
 int64_t ens_packed_decoder_floats(int level);

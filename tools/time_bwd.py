@@ -10,7 +10,7 @@ dev = 'cuda:0'
 nrays = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 scene = cases.room0_scene()
 ref = {}
-for wgrad, ggrid, tc in ((True, True, True), (True, True, False), (False, True, True), (False, False, True), (False, False, False)):
+for wgrad, ggrid, tc in ((True, True, True), (True, False, True), (True, True, False), (True, False, False), (False, True, True), (False, False, True), (False, False, False)):
     functional.TC_MAP = tc
     os.environ['ENS_BWD_TC'] = '1' if tc else '0'
     decoders, c, renderer, cfg = harness.build(scene, dev, requires_grad=wgrad)
