@@ -987,7 +987,8 @@ def measure_mapping_variants(dev, renderer, decoders, c, frames, scene):
     w0 = [p.detach().clone() for p in params]
 
     def iteration():
-        renderer._cache.invalidate()
+        # no cache invalidation needed: the optimisers bump the parameter versions, and under capture SceneCache packs
+        # inside the graph
         depth, unc, color = renderer.render_batch_ray(it_grids, decoders, rd_i, ro_i, dev, "color", gt_depth=batch[2])
         mapper_loss(batch[2], batch[3], depth, color, 0.2, True).backward()
         gopt.step({})

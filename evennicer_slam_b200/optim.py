@@ -14,8 +14,13 @@ reads the dense gradient the render backward produced (``ens_grid_adam_step``).
         opt.zero_grad()
 
 Semantics are those of the reference sequence: selected voxels (all 32 channels) take the Adam update with zero-initialised
-moments and a step count starting at 1; every other voxel keeps its value.  Learning rate 0 (a stage that freezes a level,
-configs/nice_slam.yaml:45-76) still advances the moments, exactly as torch.optim.Adam does with lr = 0.
+moments; every other voxel keeps its value.  Learning rate 0 (a stage that freezes a level, configs/nice_slam.yaml:45-76)
+still advances the moments, exactly as torch.optim.Adam does with lr = 0.  A level whose ``.grad`` is None at a step (the
+middle stage renders without grid_fine / grid_color, Mapper.py:462-473) is SKIPPED and keeps its own step count, as
+torch.optim.Adam keeps ``state['step']`` per parameter: its first update later uses step = 1.
+
+Both optimisers write the parameters through raw device pointers; they bump the tensors' autograd version counters
+afterwards (``torch.autograd.graph.increment_version``) so that version-keyed caches (``scene.SceneCache``) re-pack.
 """
 from __future__ import annotations
 
@@ -26,6 +31,11 @@ import torch
 
 from . import _lib
 from .scene import is_native_strided
+
+
+def _bump_version(t: torch.Tensor) -> None:
+    """The kernels updated ``t`` behind autograd's back: make ``t._version`` say so."""
+    torch.autograd.graph.increment_version(t)
 
 
 def _native_base(t: torch.Tensor) -> torch.Tensor:
@@ -45,7 +55,8 @@ class FrustumGridAdam:
             raise ValueError("FrustumGridAdam optimises 1..4 grids")
         self.c = c
         self.betas, self.eps = betas, eps
-        self.step_count = 0
+        self.step_count = 0                     # calls of step(); the Adam step of a level is self.steps[level]
+        self.steps = {k: 0 for k in self.keys}
         self.state = {}
         self.masks = {}
         for k in self.keys:
@@ -73,34 +84,45 @@ class FrustumGridAdam:
 
     def step(self, lrs: Dict[str, float], clear_grad: bool = False) -> None:
         L = _lib.lib()
-        n = len(self.keys)
-        arr = (_lib.EnsAdamLevel * n)()
-        keep = []
-        for i, k in enumerate(self.keys):
-            g = self.c[k]
-            grad = g.grad
-            if grad is None:
-                raise RuntimeError(f"{k}.grad is None: run the render backward before FrustumGridAdam.step")
-            if not is_native_strided(grad):       # a gradient that did not come from the fused backward
-                grad = grad.contiguous()[0].permute(1, 2, 3, 0).contiguous().permute(3, 0, 1, 2).unsqueeze(0)
-                if clear_grad:
-                    raise RuntimeError("clear_grad needs the native-layout gradient of the fused backward")
-            gb, base = _native_base(grad), _native_base(g)
-            m, v = self.state[k]
-            keep.append(gb)
-            arr[i].grid, arr[i].grad = base.data_ptr(), gb.data_ptr()
-            arr[i].exp_avg, arr[i].exp_avg_sq = m.data_ptr(), v.data_ptr()
-            arr[i].n_voxels = base.shape[0] * base.shape[1] * base.shape[2]
-            arr[i].voxel_index = None if self.masks[k] is None else self.masks[k].data_ptr()
-            arr[i].n_selected = arr[i].n_voxels if self.masks[k] is None else self.masks[k].numel()
-            arr[i].lr = float(lrs.get(k, 0.0))
+        # levels that took part in this iteration's backward; the others are skipped (torch.optim.Adam skips p.grad is None)
+        active = [k for k in self.keys if self.c[k].grad is not None]
         self.step_count += 1
+        if not active:
+            return
+        if self.dyn is not None and len(active) != len(self.keys):
+            raise RuntimeError("graph_safe FrustumGridAdam replays a fixed set of levels: capture one optimiser per stage")
+        for k in active:
+            self.steps[k] += 1
         from .functional import TIMER
-        TIMER.launches += 1
         dev = self.c[self.keys[0]].device
-        _lib.check(L.ens_grid_adam_step(arr, n, self.betas[0], self.betas[1], self.eps, self.step_count,
-                                        _lib.ptr(self.dyn), 1 if clear_grad else 0, _lib.cur_stream(dev)),
-                   "ens_grid_adam_step")
+        keep = []
+        # one launch per distinct Adam step number (one in the steady state, at most one per stage of the schedule)
+        for st in sorted({self.steps[k] for k in active}):
+            ks = [k for k in active if self.steps[k] == st]
+            n = len(ks)
+            arr = (_lib.EnsAdamLevel * n)()
+            for i, k in enumerate(ks):
+                g = self.c[k]
+                grad = g.grad
+                if not is_native_strided(grad):       # a gradient that did not come from the fused backward
+                    grad = grad.contiguous()[0].permute(1, 2, 3, 0).contiguous().permute(3, 0, 1, 2).unsqueeze(0)
+                    if clear_grad:
+                        raise RuntimeError("clear_grad needs the native-layout gradient of the fused backward")
+                gb, base = _native_base(grad), _native_base(g)
+                m, v = self.state[k]
+                keep.append(gb)
+                arr[i].grid, arr[i].grad = base.data_ptr(), gb.data_ptr()
+                arr[i].exp_avg, arr[i].exp_avg_sq = m.data_ptr(), v.data_ptr()
+                arr[i].n_voxels = base.shape[0] * base.shape[1] * base.shape[2]
+                arr[i].voxel_index = None if self.masks[k] is None else self.masks[k].data_ptr()
+                arr[i].n_selected = arr[i].n_voxels if self.masks[k] is None else self.masks[k].numel()
+                arr[i].lr = float(lrs.get(k, 0.0))
+            TIMER.launches += 1
+            _lib.check(L.ens_grid_adam_step(arr, n, self.betas[0], self.betas[1], self.eps, st,
+                                            _lib.ptr(self.dyn), 1 if clear_grad else 0, _lib.cur_stream(dev)),
+                       "ens_grid_adam_step")
+        for k in active:
+            _bump_version(self.c[k])
 
     def zero_grad(self) -> None:
         for k in self.keys:
@@ -125,8 +147,9 @@ class FusedAdam:
         if not 1 <= len(self.param_groups) <= 8:
             raise ValueError("FusedAdam takes 1..8 parameter groups")
         self.betas, self.eps = betas, eps
-        self.step_count = 0
-        flat = [p for g in self.param_groups for p in g["params"]]
+        self.step_count = 0                     # calls of step(); the Adam step of a tensor is self.steps[i] (torch keeps
+        flat = [p for g in self.param_groups for p in g["params"]]      # state['step'] per parameter: None grads are skipped)
+        self.steps = [0] * len(flat)
         if not flat:
             raise ValueError("FusedAdam got an empty parameter list")
         for p in flat:
@@ -145,27 +168,35 @@ class FusedAdam:
 
     def step(self) -> None:
         L = _lib.lib()
-        ps, gs, sizes, grp, offs = [], [], [], [], []
+        ps, gs, sizes, grp, offs, sts, tens = [], [], [], [], [], [], []
         off = 0
         keep = []
+        idx = 0
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 n = p.numel()
                 if p.grad is not None:
                     gr = p.grad if (p.grad.is_contiguous() and p.grad.dtype == torch.float32) else p.grad.float().contiguous()
                     keep.append(gr)
+                    self.steps[idx] += 1
                     ps.append(p.data_ptr()); gs.append(gr.data_ptr()); sizes.append(n); grp.append(gi); offs.append(off)
+                    sts.append(self.steps[idx]); tens.append(p)
                 off += n
+                idx += 1
         self.step_count += 1
         if not ps:
             return
+        if self.dyn is not None and len(set(sts)) != 1:
+            raise RuntimeError("graph_safe FusedAdam replays one step number for all tensors: the set of tensors with a "
+                               "gradient must not change between replays")
         from .functional import TIMER
-        # the moments of a skipped tensor must not shift the others: one call per run of consecutive state offsets
+        # the moments of a skipped tensor must not shift the others, and every tensor uses its OWN step number: one call
+        # per run of consecutive state offsets with the same step
         i = 0
         lrs = (C.c_double * len(self.param_groups))(*[g["lr"] for g in self.param_groups])
         while i < len(ps):
             j = i + 1
-            while j < len(ps) and offs[j] == offs[j - 1] + sizes[j - 1]:
+            while j < len(ps) and offs[j] == offs[j - 1] + sizes[j - 1] and sts[j] == sts[i]:
                 j += 1
             n = j - i
             TIMER.launches += 1
@@ -173,9 +204,11 @@ class FusedAdam:
                 (C.c_void_p * n)(*ps[i:j]), (C.c_void_p * n)(*gs[i:j]), (C.c_int64 * n)(*sizes[i:j]),
                 (C.c_int * n)(*grp[i:j]), n, lrs, len(self.param_groups),
                 C.c_void_p(self.exp_avg.data_ptr() + 4 * offs[i]), C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * offs[i]),
-                self.betas[0], self.betas[1], self.eps, self.step_count, _lib.ptr(self.dyn),
+                self.betas[0], self.betas[1], self.eps, sts[i], _lib.ptr(self.dyn),
                 _lib.cur_stream(self._dev)), "ens_tensors_adam_step")
             i = j
+        for p in tens:
+            _bump_version(p)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for g in self.param_groups:

@@ -116,8 +116,11 @@ class SceneCache:
             self.stats["grid_hit"] += 1
             return grid.detach()[0].permute(1, 2, 3, 0)
         key = (level, grid.device.index)
+        # inside a CUDA-graph capture the conversion must be PART of the graph (a cache hit would bake in a buffer that is
+        # never refreshed on replay and may be freed): always convert into a fresh, graph-pool buffer and cache nothing
+        capturing = torch.cuda.is_current_stream_capturing()
         e = self._grids.get(key)
-        if e is not None and e.ref() is grid and e.version == grid._version:
+        if not capturing and e is not None and e.ref() is grid and e.version == grid._version:
             self.stats["grid_hit"] += 1
             return e.native
         src = grid.detach()
@@ -131,18 +134,21 @@ class SceneCache:
         TIMER.launches += 1
         _lib.check(L.ens_grid_to_native(_lib.ptr(src), _lib.ptr(native), Z * Y * X,
                                         _lib.cur_stream(grid.device)), "ens_grid_to_native")
+        self.stats["grid_convert"] += 1
+        if capturing:
+            return native
         e = _GridEntry()
         e.ref, e.version, e.native = weakref.ref(grid), grid._version, native
         self._grids[key] = e
-        self.stats["grid_convert"] += 1
         return native
 
     # -- decoders ------------------------------------------------------------------------
     def packed_decoder(self, level: str, params: Sequence[torch.Tensor]) -> torch.Tensor:
         dev = params[0].device
         key = (level, dev.index)
+        capturing = torch.cuda.is_current_stream_capturing()      # see native_grid: pack inside the graph, cache nothing
         e = self._decs.get(key)
-        if e is not None and len(e.refs) == len(params) and all(
+        if not capturing and e is not None and len(e.refs) == len(params) and all(
                 r() is p and v == p._version for r, v, p in zip(e.refs, e.versions, params)):
             self.stats["dec_hit"] += 1
             return e.packed
@@ -165,12 +171,14 @@ class SceneCache:
         from .functional import TIMER
         TIMER.launches += 1
         _lib.check(L.ens_pack_decoder(li, arr, n, _lib.ptr(packed), _lib.cur_stream(dev)), "ens_pack_decoder")
+        self.stats["dec_pack"] += 1
+        if capturing:
+            return packed
         e = _DecEntry()
         e.refs = [weakref.ref(p) for p in params]
         e.versions = [p._version for p in params]
         e.packed = packed
         self._decs[key] = e
-        self.stats["dec_pack"] += 1
         return packed
 
 

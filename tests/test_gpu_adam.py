@@ -175,3 +175,76 @@ def test_fused_adam_matches_torch_adam_on_decoder_shaped_groups(graph_safe):
     for k, (a, b) in enumerate(zip(pa + cams, pb + camsb)):
         a, b = a.detach().cpu().numpy(), b.detach().cpu().numpy()
         assert np.all(np.abs(a - b) <= 2e-6 * 0.03 + 2 * np.spacing(np.abs(a))), (k, np.abs(a - b).max())
+
+
+def test_render_after_fused_adam_step_uses_the_updated_weights():
+    """FusedAdam / FrustumGridAdam write the parameters through raw pointers; they must bump the autograd versions so that
+    SceneCache re-packs (a stale packed decoder was used silently after the first optimiser step)."""
+    import cases
+    from evennicer_slam_b200 import harness
+    from evennicer_slam_b200.optim import FusedAdam
+    scene = cases.tiny_scene()
+    decoders, c, renderer, cfg = harness.build(scene, DEV)
+    rng = np.random.RandomState(3)
+    ro = torch.from_numpy(np.tile(np.array([[0.3, 0.2, 0.1]], np.float32), (16, 1))).to(DEV)
+    rd = torch.from_numpy((rng.randn(16, 3) * 0.3 + np.array([0.1, 0.1, -1.0])).astype(np.float32)).to(DEV)
+    gt = torch.full((16,), 1.5, device=DEV)
+    params = list(decoders.parameters())
+    opt = FusedAdam(params, lr=0.05)
+    d0, _, col0 = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=gt)
+    (d0.sum() + col0.sum().double()).backward()
+    v_before = [p._version for p in params]
+    opt.step()
+    assert all(p._version > v for p, v in zip(params, v_before) if p.grad is not None)
+    with torch.no_grad():
+        d1, _, col1 = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=gt)
+        renderer._cache.invalidate()                      # a render with freshly packed weights is the truth
+        d2, _, col2 = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=gt)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2) and torch.equal(col1, col2)
+    assert not torch.equal(col0.detach(), col1)           # and the step did change the output
+
+
+def test_staged_schedule_skips_levels_without_gradient_like_torch_adam():
+    """Mapper.py:462-473: the middle stage gives grid_fine / grid_color (and their decoders) no gradient; torch.optim.Adam
+    skips such parameters and keeps a step count per parameter."""
+    from evennicer_slam_b200 import scene as scn
+    from evennicer_slam_b200.optim import FrustumGridAdam, FusedAdam
+    rng = np.random.RandomState(5)
+    shapes = {"grid_middle": (1, 32, 4, 5, 6), "grid_fine": (1, 32, 6, 5, 7), "grid_color": (1, 32, 6, 5, 7)}
+    start = {k: (rng.randn(*s) * 0.01).astype(np.float32) for k, s in shapes.items()}
+    c = {k: scn.as_native_layout(torch.from_numpy(v).to(DEV)).requires_grad_(True) for k, v in start.items()}
+    ref = {k: torch.from_numpy(v.copy()).to(DEV).requires_grad_(True) for k, v in start.items()}
+    small = [torch.from_numpy(rng.randn(n).astype(np.float32)).to(DEV).requires_grad_(True) for n in (7, 33, 128)]
+    small_ref = [t.detach().clone().requires_grad_(True) for t in small]
+    gopt = FrustumGridAdam(c, None)
+    dopt = FusedAdam(small, lr=0.01)
+    topt = torch.optim.Adam([{"params": [ref[k]], "lr": 0.0} for k in shapes] + [{"params": small_ref, "lr": 0.01}])
+    stages = [("grid_middle",)] * 3 + [("grid_middle", "grid_fine")] * 2 + [("grid_middle", "grid_fine", "grid_color")] * 3
+    for it, live in enumerate(stages):
+        lrs = {k: 0.01 for k in live}
+        for gi, k in enumerate(shapes):
+            topt.param_groups[gi]["lr"] = lrs.get(k, 0.0)
+            if k in live:
+                g = (rng.randn(*shapes[k]) * 0.1).astype(np.float32)
+                c[k].grad = scn.as_native_layout(torch.from_numpy(g).to(DEV))
+                ref[k].grad = torch.from_numpy(g).to(DEV)
+            else:
+                c[k].grad = None
+                ref[k].grad = None
+        for j, (t, tr) in enumerate(zip(small, small_ref)):
+            if j <= len(live) - 1:                         # tensor j first gets a gradient in stage j
+                g = torch.from_numpy(rng.randn(t.numel()).astype(np.float32)).to(DEV)
+                t.grad, tr.grad = g.clone(), g.clone()
+            else:
+                t.grad, tr.grad = None, None
+        gopt.step(lrs)
+        dopt.step()
+        topt.step()
+    torch.cuda.synchronize()
+    assert gopt.steps == {"grid_middle": 8, "grid_fine": 5, "grid_color": 3}
+    for k in shapes:
+        got, want = c[k].detach().cpu().numpy(), ref[k].detach().cpu().numpy()
+        assert _close(got, want, start[k]), k
+    for t, tr in zip(small, small_ref):
+        assert torch.allclose(t.detach(), tr.detach(), rtol=2e-6, atol=1e-7)
