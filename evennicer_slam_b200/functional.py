@@ -179,6 +179,8 @@ class _RenderBatchRay(torch.autograd.Function):
             _lib.ptr(z), _lib.ptr(w), _lib.ptr(raw), _lib.ptr(saved), saved.numel() * 4 if saved is not None else 0,
             saved_kind, _lib.ptr(scratch), scratch.numel() * 8 if scratch is not None else 0,
             stream)), "ens_render_fwd")
+        if _DEBUG.get("keep_saved"):
+            _DEBUG["saved"] = (saved, saved_kind)
         ctx.saved_fwd = saved
         ctx.saved_has_h = bool(want_dec)
         ctx.saved_kind = saved_kind

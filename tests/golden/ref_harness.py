@@ -1,8 +1,8 @@
-"""Import the (read-only) Python reference from /root/reference in THIS container.
+"""Import the (read-only) Python reference: from /root/reference in the build container, else from the copy
+``baseline/install_ref.py`` put under ``baseline/_ref/`` (git-ignored; it travels to the GPU box).
 
-Used only by ``make_golden.py`` (and optional local cross-checks); nothing that
-runs on the GPU box imports this file's target, because /root/reference does not
-exist there.
+Used by ``make_golden.py`` (CPU goldens), by ``tests/test_gpu_reference.py`` (the reference on CUDA against those
+goldens) and by ``bench.py``'s ``gpu_reference`` figure.  Never by the product path.
 
 The reference cannot run on CPU unmodified: two lines build a
 ``cuda:-1`` device string.  They are patched in memory at import; the files under
@@ -21,11 +21,12 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = "/root/reference"
+_LOCAL = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/src") else _LOCAL
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "src"))
+    return os.path.isfile(os.path.join(REF_ROOT, "src", "utils", "Renderer.py"))
 
 
 def _load_patched(modname: str, relpath: str, replacements):
@@ -51,7 +52,7 @@ def load():
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
-        raise RuntimeError("/root/reference is not present")
+        raise RuntimeError("the reference is not present (neither /root/reference nor baseline/_ref)")
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import src  # noqa: F401  (the reference's package root)
@@ -84,12 +85,12 @@ def load_cfg(rel="configs/Replica/room0.yaml"):
     return cfg
 
 
-def build_reference(scene, cfg=None):
-    """Reference NICE decoders + grids + Renderer for a synthetic ``Scene`` (CPU tensors)."""
+def build_reference(scene, cfg=None, device="cpu"):
+    """Reference NICE decoders + grids + Renderer for a synthetic ``Scene`` (tensors on ``device``)."""
     ref = load()
     cfg = cfg or load_cfg()
     model = ref.onet_config.get_model(cfg, nice=True)
-    bound = torch.from_numpy(scene.bound.copy())
+    bound = torch.from_numpy(scene.bound.copy()).to(device)
     model.bound = bound
     model.middle_decoder.bound = bound
     model.fine_decoder.bound = bound
@@ -99,7 +100,8 @@ def build_reference(scene, cfg=None):
         dec = getattr(model, lv + "_decoder")
         sd = {k: torch.from_numpy(v.copy()) for k, v in scene.decoders[lv].items()}
         dec.load_state_dict(sd)
-    c = {k: torch.from_numpy(v.copy()) for k, v in scene.grids.items()}
+    model = model.to(device)
+    c = {k: torch.from_numpy(v.copy()).to(device) for k, v in scene.grids.items()}
     cam = scene.cam
     slam = types.SimpleNamespace(nice=True, bound=bound, H=cam.H, W=cam.W, fx=cam.fx, fy=cam.fy,
                                  cx=cam.cx, cy=cam.cy)

@@ -18,7 +18,12 @@ STAGES = ("coarse", "middle", "fine", "color")
 DEV = "cuda:0"
 TOL_OUT = 1e-4
 TOL_GRAD = 1e-3
-TOL_GRAD_KINK = 3e-3     # room0-scale batches only: a relu pre-activation within rounding of 0 may flip (see below)
+# room0-scale batches hold ~2e7 relu decisions, a few of them within float32 rounding of the kink.  The default path (tcgen05
+# forward + backward) differs from the reference-CPU goldens in 4 decisions and meets 1e-3 outright (measured 1.9e-4 on the
+# worst decoder tensor; the reference's own CUDA run differs from its CPU run by 2e-5: tests/test_gpu_reference.py).  Only the
+# mma.sync A/B kernels (ENS_MAP_TC=0), whose chained-register forward rounds differently, need the wider bound (1.2e-3).
+import os as _os
+TOL_GRAD_KINK = 1e-3 if _os.environ.get("ENS_MAP_TC", "1") != "0" else 3e-3
 
 
 @pytest.fixture(scope="module")
@@ -514,7 +519,9 @@ def test_rpg_sized_grids_larger_than_l2():
         assert (per_ray < TOL_GRAD).mean() >= 0.98 and per_ray.max() < 2e-2
     for k in ("grid_middle", "grid_fine", "grid_color"):
         gg = cg[k].grad.cpu().numpy()
-        assert rel_err(gg, og["grids"][k]) < TOL_GRAD_KINK, k
+        # 200 rays, not kink-screened, against the ORACLE's relu decisions: one unit on the other side of the kink is 1/9600 of
+        # the batch here (5x its weight in the 1000-ray case, which meets 1e-3 outright) -- the one place that keeps 3e-3
+        assert rel_err(gg, og["grids"][k]) < 3e-3, k
         assert int((gg != 0).sum()) == int((og["grids"][k] != 0).sum()), k
 
 
@@ -747,3 +754,81 @@ def test_small_batch_compositing_kernel_is_bit_identical(tiny):
             d2, u2, c2 = renderer.render_batch_ray(c, decoders, big_d, big_o, DEV, stage, gt_depth=None)
             assert torch.equal(d1, d2[:n]) and torch.equal(u1, u2[:n]) and torch.equal(c1, c2[:n])
             assert torch.equal(d2[:n], d2[-n:])
+
+
+def _kernel_relu_masks(saved, kind, P, ndec):
+    """relu decisions of the tcgen05 forward (saved kind 3: [relu outputs | mask words]) -> bool [ndec][5][P][32]"""
+    assert kind == 3
+    nt128 = (P + 127) // 128
+    words = saved.view(torch.int32)[ndec * nt128 * 5 * 128 * 32:].cpu().numpy().view(np.uint32)
+    nt32 = 4 * nt128
+    words = words[:ndec * nt32 * 160].reshape(ndec, nt32, 5, 32)
+    w = words.transpose(0, 2, 1, 3).reshape(ndec, 5, nt32 * 32)[:, :, :P]          # [dec][block][point]
+    return ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+
+
+def test_room0_gradients_meet_1e3_with_the_kernels_own_relu_decisions():
+    """The headline batch (1000 rays x 48 samples, colour stage, room0) at the north-star tolerance WITHOUT a relaxation.
+
+    24 M relu pre-activations: a few hundred lie within float32 rounding of zero, where two correct implementations (torch
+    CPU, cuBLAS, these kernels) may take different sides; each such flip moves the gradients by the whole contribution of
+    one unit at one point.  Here the oracle's backward is run with the relu decisions the KERNELS took (the mask words the
+    tcgen05 forward saved): every decision that differs from the oracle's own is counted and must be a unit with
+    |pre-activation| < 1e-5; with the same decisions, every gradient -- all 69 decoder tensors, the three grids, the
+    rays -- meets 1e-3, as max-norm AND elementwise (tests/util.elem_err)."""
+    from evennicer_slam_b200 import harness, functional
+    from util import elem_err
+    scene = cases.room0_scene()
+    decoders, c, renderer, cfg = harness.build(scene, DEV)
+    g = load_golden("room0_color_1000.npz")
+    cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+    ro = torch.from_numpy(g["rays_o"]).to(DEV).requires_grad_(True)
+    rd = torch.from_numpy(g["rays_d"]).to(DEV).requires_grad_(True)
+    sd = torch.from_numpy(g["sample_depth"]).to(DEV)
+    functional._DEBUG["keep_saved"] = True
+    try:
+        depth, var, color = renderer.render_batch_ray(cg, decoders, rd, ro, DEV, "color", gt_depth=sd)
+        saved, kind = functional._DEBUG.pop("saved")
+    finally:
+        functional._DEBUG.pop("keep_saved", None)
+    if kind != 3:
+        pytest.skip("the tcgen05 mapping path is switched off (ENS_MAP_TC=0)")
+    g_d, g_v, g_c = cases.upstream_grads(cases.N_ROOM0_RAYS)
+    ((depth * torch.from_numpy(g_d).to(DEV)).sum() + (var * torch.from_numpy(g_v).to(DEV)).sum()
+     + (color.double() * torch.from_numpy(g_c).double().to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    sc = orc.OracleScene.from_synthetic(scene)
+    t32 = torch.linspace(0., 1., 32).numpy(); t64 = torch.linspace(0., 1., 16).double().numpy()
+    od, ov, oc, cache = orc.render_batch_ray(sc, g["rays_o"], g["rays_d"], "color", g["sample_depth"], t32, t64)
+    P = cache["R"] * cache["S"]
+    masks = _kernel_relu_masks(saved, kind, P, 3)
+    flips = 0
+    for d, name in enumerate(("middle", "fine", "color")):
+        acts = cache["caches"][name]["mlp"]["acts"]
+        for i in range(5):
+            x, u = acts[i]
+            km = masks[d, i]                                        # [P][32]
+            diff = km != (u > 0)
+            flips += int(diff.sum())
+            assert np.abs(u[diff]).max(initial=0.0) < 1e-5, (name, i, float(np.abs(u[diff]).max()))
+            mag = np.maximum(np.abs(u), np.float32(1e-30))
+            acts[i] = (x, np.where(km, mag, -mag).astype(np.float32))
+    assert flips < 2000, flips                                      # of 23 M decisions
+    og = orc.render_batch_ray_backward(sc, cache, g_d, g_v, g_c)
+    worst = {}
+    for name in ("middle", "fine", "color"):
+        for key, p in getattr(decoders, name + "_decoder").named_parameters():
+            ref = og["decoders"][name][key]
+            if np.abs(ref).max() > 0:
+                got = p.grad.cpu().numpy()
+                worst[f"{name}.{key}"] = (rel_err(got, ref), elem_err(got, ref))
+        gk = "grid_" + name
+        got, ref = cg[gk].grad.cpu().numpy(), og["grids"][gk]
+        worst[gk] = (rel_err(got, ref), elem_err(got, ref))
+        assert int((got != 0).sum()) == int((ref != 0).sum()), gk
+    worst["rays_o"] = (rel_err(ro.grad.cpu().numpy(), og["rays_o"]), elem_err(ro.grad.cpu().numpy(), og["rays_o"]))
+    worst["rays_d"] = (rel_err(rd.grad.cpu().numpy(), og["rays_d"]), elem_err(rd.grad.cpu().numpy(), og["rays_d"]))
+    bad = {k: v for k, v in worst.items() if v[0] >= TOL_GRAD or v[1] >= TOL_GRAD}
+    print("relu decisions that differ from the oracle's:", flips, " worst max-norm / elementwise error:",
+          max(v[0] for v in worst.values()), max(v[1] for v in worst.values()))
+    assert not bad, bad

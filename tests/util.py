@@ -18,6 +18,21 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / den)
 
 
+def elem_err(a, b, floor=2e-2):
+    """ELEMENTWISE relative error with an absolute floor:  max_i |a_i - b_i| / (|b_i| + floor * max|b|).
+
+    ``rel_err`` is relative to the tensor's largest entry, so a small entry could be badly off and pass; here every entry
+    is held relative to its own size.  The floor: a gradient entry is a sum over ~5e4 float32 terms whose rounding error
+    scales with the TERMS (eps * sqrt(N) * rms ~ 1e-5 of the tensor's largest entry, measured 7e-6 between the kernels and
+    the float32 oracle), not with the entry, which cancellation can make arbitrarily small -- in the reference's own
+    atomics as in the kernels'.  With floor = 2e-2 an entry of 2 % of the largest must be right to 5e-4 of ITSELF at
+    tolerance 1e-3, and no entry may be off by more than 2e-5 of the largest."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b) + floor * max(np.abs(b).max(), 1e-30)
+    return float((np.abs(a - b) / den).max())
+
+
 def torch_t_vals(n_samples=32, n_surface=16, device="cpu"):
     """The reference's own linspace calls (Renderer.py:127-128, 153)."""
     import torch
