@@ -154,6 +154,83 @@ def oracle_step(sc, frames, n_per_frame, seed, t32, t64):
     return ro.shape[0]
 
 
+class ReferenceStepper:
+    """The mapping step through the UNMODIFIED reference modules (baseline/install_ref.py -> baseline/_ref, or
+    /root/reference): get_samples -> Renderer.render_batch_ray -> Mapper loss (Mapper.py:553-562, boolean mask) -> backward
+    into grids, decoder weights and the camera tensors.  device 'cpu' = the reference arm / cpu_baseline; 'cuda:k' = the
+    eager-PyTorch-on-B200 figure."""
+
+    def __init__(self, device):
+        import torch
+        import ref_harness as rh
+        self.torch, self.dev = torch, device
+        scene, frames = make_inputs()
+        self.ref = rh.load()
+        self.model, c, self.renderer, self.cfg = rh.build_reference(scene, device=device)
+        self.cam = scene.cam
+        self.c = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+        self.depth = [torch.from_numpy(d).to(device) for (_, d, _) in frames]
+        self.color = [torch.from_numpy(col).to(device) for (_, _, col) in frames]
+        self.cams = [torch.from_numpy(ct.copy()).to(device).requires_grad_(f > 0) for f, (ct, _, _) in enumerate(frames)]
+
+    def step(self, n_per_frame, seed):
+        torch, cam = self.torch, self.cam
+        torch.manual_seed(seed)
+        for t in list(self.c.values()) + list(self.model.parameters()) + self.cams:
+            t.grad = None
+        ros, rds, sds, scs = [], [], [], []
+        for f in range(len(self.cams)):
+            c2w = self.ref.common.get_camera_from_tensor(self.cams[f])
+            ro, rd, sd, sc = self.ref.common.get_samples(0, cam.H, 0, cam.W, n_per_frame, cam.H, cam.W, cam.fx, cam.fy,
+                                                         cam.cx, cam.cy, c2w, self.depth[f], self.color[f], self.dev)
+            ros.append(ro.float()); rds.append(rd.float()); sds.append(sd.float()); scs.append(sc.float())
+        ro, rd, sd, sc = torch.cat(ros), torch.cat(rds), torch.cat(sds), torch.cat(scs)
+        depth, unc, color = self.renderer.render_batch_ray(self.c, self.model, rd, ro, self.dev, "color", gt_depth=sd)
+        mask = sd > 0
+        loss = torch.abs(sd - depth)[mask].sum() + 0.2 * torch.abs(sc - color).sum()
+        loss.backward()
+        return ro.shape[0]
+
+
+def reference_available():
+    try:
+        import ref_harness as rh
+        return rh.available()
+    except Exception:
+        return False
+
+
+def measure_gpu_reference(dev, steps=5):
+    """The reference's own eager-PyTorch renderer on the SAME GPU, same inputs and step as the headline."""
+    import torch
+    if not reference_available():
+        return {"unavailable": "reference modules not present (baseline/install_ref.py was not run in the build container)"}
+    st = ReferenceStepper(str(dev))
+    for w in range(2):
+        st.step(PIX_PER_FRAME, w)
+    torch.cuda.synchronize()
+    evs = []
+    for k in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); st.step(PIX_PER_FRAME, 100 + k); b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    launches = None
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            st.step(PIX_PER_FRAME, 999)
+            torch.cuda.synchronize()
+        launches = sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in e.name.lower()
+                       and "memset" not in e.name.lower())
+    except Exception:
+        pass
+    return {"rays_per_s": N_RAYS / (ms * 1e-3), "ms_per_step": ms, "launches": launches, "steps": steps,
+            "what": "unmodified reference (src/common.py, src/conv_onet, src/utils/Renderer.py) in eager PyTorch on this GPU: "
+                    "get_samples + render_batch_ray + Mapper loss + backward, same scene / frames / 1000-ray colour-stage step"}
+
+
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -178,9 +255,39 @@ def use_all_host_threads():
         pass
 
 
-def cpu_baseline(budget_s=12.0):
-    """Bounded sample of the mapping workload on the host cores (kind 'port': numpy oracle)."""
+def cpu_reference_sample(budget_s, steps=None, warmup=0):
+    """Bounded sample of the mapping step through the REAL reference on the host cores (kind 'reference')."""
     import torch
+    use_all_host_threads()
+    st = ReferenceStepper("cpu")
+    st.step(4, 0)                                        # one-time costs (allocator, thread pools) stay out of the probe
+    t0 = time.perf_counter()
+    n = st.step(20, 1)
+    rate = n / (time.perf_counter() - t0)
+    if steps is None:
+        n_pf = int(max(10, min(PIX_PER_FRAME, rate * budget_s / N_FRAMES)))
+        steps = int(max(1, min(40, budget_s * rate / max(n_pf * N_FRAMES, 1))))
+    else:
+        n_pf = int(max(4, min(PIX_PER_FRAME, rate * (budget_s / max(steps + warmup, 1)) / N_FRAMES)))
+    for w in range(warmup):
+        st.step(n_pf, 10 + w)
+    t0 = time.perf_counter()
+    n = 0
+    for r in range(steps):
+        n += st.step(n_pf, 100 + r)
+    dt = time.perf_counter() - t0
+    return n / dt, n, steps, n_pf, dt, torch.get_num_threads()
+
+
+def cpu_baseline(budget_s=12.0):
+    """Bounded sample of the mapping workload on the host cores: the reference itself when its modules are present
+    (kind 'reference'), else the numpy oracle port (kind 'port')."""
+    import torch
+    if reference_available():
+        val, n, reps, n_pf, dt, thr = cpu_reference_sample(budget_s)
+        return {"value": val, "unit": "rays/s", "cores": thr, "kind": "reference",
+                "sample": f"{n} rays = {reps} x ({N_FRAMES} frames x {n_pf} px) of the {N_RAYS}-ray colour-stage mapping batch, "
+                          f"fwd+bwd, the reference's own PyTorch CPU renderer (baseline/_ref), {dt:.1f} s", "host_cpus": os.cpu_count()}
     use_all_host_threads()
     import render_oracle as orc
     scene, frames = make_inputs()
@@ -209,6 +316,21 @@ def run_reference_arm(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if reference_available():
+        val, n, steps, n_pf, dt, thr = cpu_reference_sample(150.0, steps=args.steps, warmup=args.warmup)
+        emit({
+            "impl": "reference", "metric": "rays/sec (fwd+bwd) on the Replica mapping batch", "value": val,
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (f64 sample placement / depth sums)", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": thr, "kind": "reference",
+                             "sample": f"{n_pf * N_FRAMES} rays per step of the {N_RAYS}-ray batch, the reference's own PyTorch "
+                                       "CPU renderer (unmodified modules under baseline/_ref)", "host_cpus": os.cpu_count()},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        })
         return
     use_all_host_threads()
     import render_oracle as orc
@@ -425,13 +547,19 @@ def run_gpu_arm(args):
         n_b, t_b = ksum.get("render_bwd", (0, float("nan")))
         n_f, t_f = ksum.get("render_fwd", (0, float("nan")))
         achieved = BYTES_PER_POINT_BWD * N_RAYS * S_TOTAL / (t_b * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "ens_render_bwd: render_bwd_mma_kernel<color, split> + wgrad_split_kernel<color>", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "ens_render_bwd: bwd_tc_wg_kernel<color> (tcgen05 data + weight gradients) with its placement / compositing-backward / unfold / ray-reduce launches" if functional.TC_MAP else "ens_render_bwd: render_bwd_mma_kernel<color, split> + wgrad_split_kernel<color>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(),
                 "peak_source": peak_src, "kernel_ms": t_b, "kernel_share_of_step": t_b / ms_per_step,
                 "fwd_kernel_ms": t_f, "fwd_achieved_gbs": BYTES_PER_POINT_FWD * N_RAYS * S_TOTAL / (t_f * 1e-3) / 1e9,
                 "step_algorithmic_gbs": BYTES_PER_RAY * N_RAYS / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": BYTES_PER_RAY * N_RAYS / (ms_per_step * 1e-3) / 1e9 / peak}
         cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
+        gpu_ref = None
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                gpu_ref = measure_gpu_reference(dev)
+            except Exception as e:          # pragma: no cover - reported, never fatal for the headline
+                gpu_ref = {"error": repr(e)}
         line = {
             "metric": "rays/sec (fwd+bwd) on the Replica mapping batch", "value": value, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -439,7 +567,7 @@ def run_gpu_arm(args):
             "dtype": "f32 (f64 sample placement / depth sums)", "data": "synthetic",
             "config": workload_config(), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches_timed, "gpu_launches_per_step": launches_timed / args.steps,
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
             "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms,
             "tracking_ms_per_iter_fused_loss": track_fused, "other_configs": other, "wall_s_timed_region": t_wall,
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
@@ -1088,6 +1216,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's eager-PyTorch renderer on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the event-render / full-frame / mesh timings")
     ap.add_argument("--no-frame-streams", dest="frame_streams", action="store_false",
