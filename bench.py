@@ -507,6 +507,54 @@ def run_gpu_arm(args):
         eager_ms = sum(a.elapsed_time(b) for a, b in evs2) / args.steps
     launches_timed = TIMER.launches
     ksum = TIMER.summary()
+    # ---- the drop-in path an UNCHANGED Mapper.py takes: eager launches, the callers' own lines (inside_mask pre-filter with
+    #      boolean indexing, boolean-mask loss: Mapper.py:523-578), autograd plumbing in the C++ extension ----
+    bound_dev = torch.from_numpy(scene.bound.copy()).to(dev)
+
+    def step_caller():
+        renderer._cache.invalidate()
+        ros, rds, sds, scs = [], [], [], []
+        for f in range(N_FRAMES):
+            ct = cams[0] if f == 0 else cam_params[f - 1]
+            c2w = common.get_camera_from_tensor(ct)
+            ro, rd, sd, sc_ = common.get_samples(0, cam.H, 0, cam.W, PIX_PER_FRAME, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy,
+                                                 c2w, depth_t[f], color_t[f], dev)
+            ros.append(ro.float()); rds.append(rd.float()); sds.append(sd.float()); scs.append(sc_.float())
+        batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color = torch.cat(ros), torch.cat(rds), torch.cat(sds), torch.cat(scs)
+        with torch.no_grad():
+            det_rays_o = batch_rays_o.clone().detach().unsqueeze(-1)
+            det_rays_d = batch_rays_d.clone().detach().unsqueeze(-1)
+            t = (bound_dev.unsqueeze(0) - det_rays_o) / det_rays_d
+            t, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
+            inside_mask = t >= batch_gt_depth
+        batch_rays_d = batch_rays_d[inside_mask]; batch_rays_o = batch_rays_o[inside_mask]
+        batch_gt_depth = batch_gt_depth[inside_mask]; batch_gt_color = batch_gt_color[inside_mask]
+        depth, unc, color = renderer.render_batch_ray(grids, decoders, batch_rays_d, batch_rays_o, dev, "color", gt_depth=batch_gt_depth)
+        depth_mask = (batch_gt_depth > 0)
+        loss = torch.abs(batch_gt_depth[depth_mask] - depth[depth_mask]).sum() + 0.2 * torch.abs(batch_gt_color - color).sum()
+        loss.backward()
+        return loss
+
+    from evennicer_slam_b200 import _ext
+    ext = _ext.module() if _ext.ENABLED else None
+    for _ in range(3):
+        zero_grads(); step_caller()
+    torch.cuda.synchronize()
+    if ext is not None:
+        ext.reset_launches()
+    l0 = TIMER.launches
+    evs3 = []
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        zero_grads()
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step_caller(); b.record()
+        evs3.append((a, b))
+    torch.cuda.synchronize()
+    caller_wall_ms = (time.perf_counter() - tw0) * 1e3 / args.steps
+    caller_ms = sum(a.elapsed_time(b) for a, b in evs3) / args.steps
+    caller_launches = (TIMER.launches - l0 + (ext.launches() if ext is not None else 0)) / args.steps
     # the timed region is ~K x 0.6 ms, shorter than one nvidia-smi sampling period: keep the same load (untimed runs of the
     # same step) going for ~0.5 s more so the clocks line holds several samples taken UNDER this load.  A fixed count on
     # EVERY rank: the step contains collectives when world > 1.
@@ -571,7 +619,12 @@ def run_gpu_arm(args):
             "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms,
             "tracking_ms_per_iter_fused_loss": track_fused, "other_configs": other, "wall_s_timed_region": t_wall,
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
-            "ms_per_step_eager": eager_ms,
+            "ms_per_step_eager": caller_ms,
+            "eager": {"ms_per_step": caller_ms, "wall_ms_per_step": caller_wall_ms, "c_abi_calls_per_step": caller_launches,
+                      "plumbing": "torch C++ extension (csrc/ens_torch.cpp)" if ext is not None else "python autograd.Function + ctypes",
+                      "what": "the step as an unchanged Mapper.py runs it: eager launches, per-keyframe get_samples, inside_mask "
+                              "pre-filter and boolean-mask loss (Mapper.py:523-578), backward; L2 flushed between steps",
+                      "ms_per_step_python_plumbing": eager_ms},
         }
         emit(line)
     if world > 1:
@@ -690,17 +743,43 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
     for p in decoders.parameters():
         p.requires_grad_(False)
 
-    def it():
-        ct.grad = None
+    bound_dev = torch.from_numpy(scene.bound.copy()).to(dev)
+
+    def rgbd_branch():
+        # Tracker.py:159-197 as the unchanged caller runs it: pixel draw, inside_mask pre-filter, render, boolean-mask loss
         c2w = common.get_camera_from_tensor(ct)
         ro, rd, sd, sc_ = common.get_samples(100, cam.H - 100, 100, cam.W - 100, 200, cam.H, cam.W, cam.fx, cam.fy,
                                              cam.cx, cam.cy, c2w, depth_t, color_t, dev)
+        with torch.no_grad():
+            t = (bound_dev.unsqueeze(0) - ro.clone().detach().unsqueeze(-1)) / rd.clone().detach().unsqueeze(-1)
+            t, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
+            inside_mask = t >= sd
+        rd, ro, sd, sc_ = rd[inside_mask], ro[inside_mask], sd[inside_mask], sc_[inside_mask]
         d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, dev, "color", gt_depth=sd)
         u = u.detach()
         tmp = torch.abs(sd - d) / torch.sqrt(u + 1e-10)
         mask = (tmp < 10 * tmp.median()) & (sd > 0)
         loss = (torch.abs(sd - d) / torch.sqrt(u + 1e-10))[mask].sum() + 0.5 * torch.abs(sc_ - col)[mask].sum()
+        return c2w, loss
+
+    def it():
+        ct.grad = None
+        _, loss = rgbd_branch()
         loss.backward()
+
+    ev_w = torch.rand((int(cam.H * 0.15), int(cam.W * 0.15), 3), device=dev) - 0.5
+    topt = torch.optim.Adam([ct], lr=1e-3)
+
+    def it_full():
+        # one WHOLE tracking iteration (Tracker.py:104-245) without the UNet: the event branch's down-scaled full-frame
+        # render with gradient (18 360 rays, :150) -- the UNet and its blurred loss replaced by a fixed linear functional of
+        # the rendered colour, so the render backward runs as in the real iteration -- plus the RGB-D branch and Adam.step
+        topt.zero_grad()
+        c2w, loss_rgbd = rgbd_branch()
+        _, _, full_color = renderer.render_img_rescale(c, decoders, c2w, dev, "color", gt_depth=depth_t, scale_factor=0.15)
+        loss_rgbd.backward(retain_graph=True)
+        (full_color * ev_w).sum().backward()
+        topt.step()
 
     def it_capturable():
         # the same iteration without host synchronisation: the boolean-mask selections become where() sums
@@ -744,6 +823,12 @@ def measure_tracking(dev, renderer, decoders, c, frames, scene, flush, iters=20)
     eager_ms = timed(it)
     graph_ms = None
     fused = {}
+    try:
+        fused["full_iteration_eager_ms"] = timed(it_full)
+        fused["full_iteration_what"] = ("RGB-D branch (200 px) + event-branch render_img_rescale fwd+bwd (18 360 rays, pose "
+                                        "gradient) + torch Adam.step on the camera tensor; UNet excluded")
+    except Exception as e:      # pragma: no cover
+        fused["full_iteration_error"] = repr(e)
     try:
         from evennicer_slam_b200.graph import GraphedStep
         graph_ms = timed(GraphedStep(it_capturable, warmup=2, device=dev))

@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import torch
 
-from .functional import _LatticeRays, _SampleRays, _c2w_dev
+from . import _ext
+from .functional import TIMER, _LatticeRays, _SampleRays, _c2w_dev
 
 _LIN_CACHE = {}
 
@@ -27,6 +28,10 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
     """Get n rays from the image region H0..H1, W0..W1 (common.py:160-169)."""
     indices = torch.randint((H1 - H0) * (W1 - W0), (n,), device=device)     # common.py:99
     c2w = _c2w_dev(c2w, device)
+    ext = _ext.module() if (_ext.ENABLED and not TIMER.enabled) else None
+    if ext is not None:                                                     # autograd plumbing in C++ (csrc/ens_torch.cpp)
+        return tuple(ext.sample_rays(c2w, indices, depth, color, [int(H0), int(H1), int(W0), int(W1)],
+                                     [float(H), float(W), float(fx), float(fy), float(cx), float(cy)]))
     rays_o, rays_d, sample_depth, sample_color = _SampleRays.apply(
         c2w, indices, (int(H0), int(H1), int(W0), int(W1)),
         (int(H), int(W), float(fx), float(fy), float(cx), float(cy)), depth, color)
@@ -80,6 +85,9 @@ def get_camera_from_tensor(inputs):
     """[quat, T] (7) -> (3,4) [R|t] (common.py:215-228).  CUDA float32 tensors take the fused kernel
     (one launch forward, one backward, instead of ~60 eager ops per pose)."""
     if inputs.is_cuda and inputs.dtype == torch.float32:
+        ext = _ext.module() if (_ext.ENABLED and not TIMER.enabled) else None
+        if ext is not None:
+            return ext.pose_to_c2w(inputs.unsqueeze(0))[0] if inputs.dim() == 1 else ext.pose_to_c2w(inputs)
         from .functional import _PoseToC2W
         if inputs.dim() == 1:
             return _PoseToC2W.apply(inputs.unsqueeze(0))[0]

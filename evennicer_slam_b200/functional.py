@@ -11,7 +11,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import _lib
+from . import _ext, _lib
 from ._lib import LEVELS, STAGES, STAGE_LEVELS, EnsGrads, EnsRenderCfg
 from .scene import SceneCache, build_scene_struct, decoder_grad_views, is_native_strided
 
@@ -128,7 +128,8 @@ class _RenderBatchRay(torch.autograd.Function):
             native[lv] = setup.cache.native_grid(lv, g)
             n = L.ens_decoder_num_tensors(LEVELS.index(lv))
             per_level_params[lv] = params[off:off + n]
-            packed[lv] = setup.cache.packed_decoder(lv, per_level_params[lv])
+            live = getattr(setup, "_cache_params", None)
+            packed[lv] = setup.cache.packed_decoder(lv, live[off:off + n] if live is not None else per_level_params[lv])
             off += n
         sc = build_scene_struct(setup.bound, setup.coarse_bound, native, packed)
         cfg = setup.cfg_struct()
@@ -300,8 +301,24 @@ class _RenderBatchRay(torch.autograd.Function):
         return tuple(out)
 
 
+_EMPTY: Dict[str, torch.Tensor] = {}
+
+
+def _empty_on(dev) -> torch.Tensor:
+    t = _EMPTY.get(str(dev))
+    if t is None:
+        t = torch.empty(0, dtype=torch.float32, device=dev)
+        _EMPTY[str(dev)] = t
+    return t
+
+
+def _bounds12(bound: torch.Tensor, coarse_bound: torch.Tensor) -> List[float]:
+    from .scene import _bound_floats
+    return list(_bound_floats(bound)) + list(_bound_floats(coarse_bound))
+
+
 def render_batch_ray(setup: RenderSetup, c: Dict[str, torch.Tensor], decoders, rays_d, rays_o, gt_depth=None,
-                     want_aux: bool = False, depth_max: Optional[torch.Tensor] = None):
+                     want_aux: bool = False, depth_max: Optional[torch.Tensor] = None, freeze_params: bool = False):
     """Fused Renderer.render_batch_ray.  Returns (depth f64, var f64, color f32[, raw, z_vals, weights])."""
     from .scene import decoder_tensors
     levels = STAGE_LEVELS[setup.stage]
@@ -309,6 +326,9 @@ def render_batch_ray(setup: RenderSetup, c: Dict[str, torch.Tensor], decoders, r
     params: List[torch.Tensor] = []
     for lv in levels:
         params.extend(decoder_tensors(decoders, lv))
+    cache_params = params              # SceneCache keys the packed blobs on the identity / version of the live Parameters
+    if freeze_params:                  # Renderer.decoder_grads = False: the weights are constants of this render
+        params = [p.detach() for p in params]
     has_depth = gt_depth is not None and setup.stage != "coarse"
     if has_depth:
         gt_depth = gt_depth.reshape(-1)
@@ -318,8 +338,36 @@ def render_batch_ray(setup: RenderSetup, c: Dict[str, torch.Tensor], decoders, r
             depth_max = depth_batch_max(gt_depth.contiguous())
     else:
         depth_max = None
-    out = _RenderBatchRay.apply(setup, gt_depth if has_depth else None, depth_max, len(grids), levels, want_aux,
-                                rays_o, rays_d, *grids, *params)
+    ext = _ext.module() if (_ext.ENABLED and not TIMER.enabled) else None
+    if ext is not None and setup.n_importance == 0 and not setup.lindisp and setup.perturb == 0 and setup.occupancy \
+            and not _DEBUG:
+        # the same sequence as _RenderBatchRay below with the autograd plumbing in C++ (csrc/ens_torch.cpp): the layouts the
+        # kernels read are prepared here (SceneCache: version-checked), everything per call happens there
+        L = _lib.lib()
+        native, packed, n_params = [], [], []
+        off = 0
+        for lv, g in zip(levels, grids):
+            n = L.ens_decoder_num_tensors(LEVELS.index(lv))
+            native.append(setup.cache.native_grid(lv, g))
+            packed.append(setup.cache.packed_decoder(lv, cache_params[off:off + n]))
+            n_params.append(n)
+            off += n
+        dev = rays_o.device
+        empty = _empty_on(dev)
+        aux = [gt_depth if has_depth else empty, depth_max if has_depth else empty, setup.t_vals,
+               setup.t_surf if setup.t_surf is not None else empty]
+        out = ext.render(rays_o, rays_d, grids, params, aux, native, packed, STAGES[setup.stage], setup.n_samples,
+                         setup.n_surface, _bounds12(setup.bound, setup.coarse_bound), n_params, want_aux, TC_MAP,
+                         TC_POSE_FORWARD)
+        if want_aux:
+            return tuple(out)
+        return out[0], out[1], out[2]
+    setup._cache_params = cache_params
+    try:
+        out = _RenderBatchRay.apply(setup, gt_depth if has_depth else None, depth_max, len(grids), levels, want_aux,
+                                    rays_o, rays_d, *grids, *params)
+    finally:
+        setup._cache_params = None
     if want_aux:
         return out
     return out[0], out[1], out[2]

@@ -23,6 +23,11 @@ from .scene import SceneCache
 class Renderer(object):
     def __init__(self, cfg, args, slam, points_batch_size=500000, ray_batch_size=100000):
         self.ray_batch_size = ray_batch_size
+        # Opt-in for the TRACKER's renderer (one line in Tracker.__init__: ``self.renderer.decoder_grads = False``): its
+        # decoders are a deepcopy with requires_grad=True (Tracker.py:248-260) that no optimiser ever steps, so the reference
+        # computes a weight-gradient pass nobody reads.  False = render with the decoder weights as constants: the pose-only
+        # backward (no weight-gradient GEMMs, no activations kept), whatever requires_grad says.
+        self.decoder_grads = True
         self.points_batch_size = points_batch_size      # kept for API parity; the fused kernel has no
                                                         # per-point HBM intermediates, so no point chunking
         self.lindisp = cfg['rendering']['lindisp']
@@ -76,7 +81,7 @@ class Renderer(object):
         Returns depth (N,) float64, uncertainty (N,) float64, color (N,3) float32.
         """
         setup = self._setup(stage, decoders, rays_o.device)
-        return _render_batch_ray(setup, c, decoders, rays_d, rays_o, gt_depth)
+        return _render_batch_ray(setup, c, decoders, rays_d, rays_o, gt_depth, freeze_params=not self.decoder_grads)
 
     def render_batch_ray_aux(self, c, decoders, rays_d, rays_o, device, stage, gt_depth=None):
         """render_batch_ray that also returns (raw, z_vals, weights) -- used by the parity tests."""
