@@ -450,8 +450,18 @@ def run_gpu_arm(args):
         loss = torch.where(sd > 0, torch.abs(sd - depth), 0.0).sum() + 0.2 * torch.abs(sc_ - color).sum()
         loss.backward()
         if world > 1:
-            sharding.allreduce_sum_([t.grad for t in list(grids.values()) + params + cam_params])
+            if sparse_ar is not None:
+                # only the voxels some rank touched cross NVLink (sharding.SparseGradAllReduce)
+                sparse_ar([grids[k].grad for k in ar_keys],
+                          [grids[k].grad for k in grids if k not in ar_keys] + [t.grad for t in params + cam_params])
+            else:
+                sharding.allreduce_sum_([t.grad for t in list(grids.values()) + params + cam_params])
         return loss
+
+    ar_keys = [k for k in grids if "coarse" not in k]
+    sparse_ar = None
+    if world > 1 and not args.reference_grid_layout and not args.dense_allreduce:
+        sparse_ar = sharding.SparseGradAllReduce([grids[k] for k in ar_keys], capacity_frac=0.2)
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
@@ -618,6 +628,8 @@ def run_gpu_arm(args):
             "roofline": roof, "cpu_baseline": cpu, "gpu_reference": gpu_ref,
             "tracking_ms_per_iter": track_ms, "tracking_ms_per_iter_graph": track_graph_ms,
             "tracking_ms_per_iter_fused_loss": track_fused, "other_configs": other, "wall_s_timed_region": t_wall,
+            "allreduce": (None if world == 1 else ("touched voxels only (sharding.SparseGradAllReduce, capacity 20 % of the voxels; "
+                          f"overflowed: {sparse_ar.overflowed()})" if sparse_ar is not None else "dense gradient arena")),
             "launch_mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "ms_per_step_eager": caller_ms,
             "eager": {"ms_per_step": caller_ms, "wall_ms_per_step": caller_wall_ms, "c_abi_calls_per_step": caller_launches,
@@ -633,6 +645,15 @@ def run_gpu_arm(args):
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush(); sys.stderr.flush()
+        # release the captured graphs (they hold NCCL work) before the communicator goes away, then tear down properly; a
+        # watchdog keeps a wedged destroy_process_group from hanging the launcher (the line is already printed)
+        import gc
+        import threading
+        run_step = None
+        gc.collect()
+        torch.cuda.synchronize()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
         os._exit(0)
 
 
@@ -888,7 +909,55 @@ def measure_sharded_frame(dev, renderer, decoders, c, frames, scene, world):
         res["mesh_lattice_sharded"] = measure_sharded_mesh(dev, renderer, decoders, c, scene, world)
     except Exception as e:          # pragma: no cover - reported in place
         res["mesh_lattice_sharded"] = {"error": repr(e)}
+    try:
+        res["mapping_large_batch_sharded"] = measure_sharded_large_batch(dev, renderer, decoders, c, frames, scene, world)
+    except Exception as e:          # pragma: no cover - reported in place
+        res["mapping_large_batch_sharded"] = {"error": repr(e)}
     return res
+
+
+def measure_sharded_large_batch(dev, renderer, decoders, c, frames, scene, world):
+    """STRONG scaling of large-batch mapping (north_star: "large-batch mapping also shards rays across GPUs, replicating the
+    grids and all-reducing their gradients"): the SAME 65 535-ray colour-stage batch on N GPUs, every rank renders
+    and back-propagates its contiguous shard (the two depth maxima taken over the whole batch, so sample placement is that
+    of the unsharded batch), the gradients are SUM all-reduced (touched voxels only).  All ranks call this."""
+    import torch
+    import torch.distributed as dist
+    from evennicer_slam_b200 import sharding
+    from evennicer_slam_b200.functional import depth_batch_max, render_batch_ray
+    from evennicer_slam_b200.scene import as_native_layout
+    n_big = 65536 // N_FRAMES * N_FRAMES
+    ro, rd, sd, sc_ = _mapping_batch(dev, scene, frames, n_big, 32)
+    rank = dist.get_rank()
+    lo, hi = sharding.shard_range(n_big, rank, world)
+    grids = {k: as_native_layout(v.detach().clone()).requires_grad_(True) for k, v in c.items()}
+    params = [p for p in decoders.parameters()]
+    keys = [k for k in grids if "coarse" not in k]
+    ar = sharding.SparseGradAllReduce([grids[k] for k in keys], capacity_frac=0.6)
+    dmax = depth_batch_max(sd.contiguous())
+    setup = renderer._setup("color", decoders, dev)
+    ro_l = ro[lo:hi].clone().requires_grad_(True); rd_l = rd[lo:hi].clone().requires_grad_(True)
+
+    def step():
+        for t in [ro_l, rd_l] + list(grids.values()) + params:
+            t.grad = None
+        depth, unc, color = render_batch_ray(setup, grids, decoders, rd_l, ro_l, sd[lo:hi], depth_max=dmax)
+        loss = torch.where(sd[lo:hi] > 0, torch.abs(sd[lo:hi] - depth), 0.0).sum() + 0.2 * torch.abs(sc_[lo:hi] - color).sum()
+        loss.backward()
+        ar([grids[k].grad for k in keys], [p.grad for p in params])
+    step(); step()
+    torch.cuda.synchronize(); dist.barrier()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        step()
+    e.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(e) / 3], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"rays": n_big, "n_gpus": world, "ms": ms, "rays_per_s": n_big / ms * 1e3, "scaling": "strong",
+            "allreduce_overflowed": ar.overflowed(),
+            "frac_of_hbm_roofline_per_gpu": n_big / ms * 1e3 * BYTES_PER_RAY / (hbm_peak()[0] * 1e9) / world}
 
 
 def measure_sharded_mesh(dev, renderer, decoders, c, scene, world):
@@ -1356,6 +1425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-allreduce", action="store_true", help="N > 1: all-reduce the whole gradient arena instead of the touched voxels")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the reference's eager-PyTorch renderer on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the event-render / full-frame / mesh timings")

@@ -49,6 +49,9 @@ class EnsGrads(C.Structure):
 _SIGNATURES = {
     "ens_version": (C.c_int, []),
     "ens_strerror": (C.c_char_p, [C.c_int]),
+    "ens_grid_touched": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ens_grid_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                   C.c_void_p]),
     "ens_last_error": (C.c_char_p, []),
     "ens_packed_decoder_floats": (C.c_int64, [C.c_int]),
     "ens_decoder_grad_floats": (C.c_int64, [C.c_int]),

@@ -220,6 +220,17 @@ typedef struct EnsAdamLevel {
 int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels, double beta1, double beta2, double eps,
                        int64_t step, const double *dyn, int clear_grad, ens_stream_t stream);
 
+/* ---- sharded mapping step: exchange only the voxels some rank touched ---------------------------------------
+ * grad: a native-layout gradient [n_vox][32] as ens_render_bwd accumulates it.
+ * ens_grid_touched: flags[v] = 1 iff voxel v has a non-zero channel (device int32 [n_vox], overwritten).
+ * ens_grid_compact: with flags MAX-reduced over the ranks and pos = their inclusive prefix sum (device int32 [n_vox], over all
+ * levels that share `compact`), to_compact != 0 copies the flagged rows to compact[pos[v] - 1] ([capacity][32] floats);
+ * to_compact == 0 copies them back (after the SUM all-reduce of `compact`).  Rows past `capacity` are left alone and counted
+ * in *overflow (device int32, accumulated): a caller that sees it non-zero must fall back to the dense all-reduce. */
+int ens_grid_touched(const float *grad, int64_t n_vox, int32_t *flags, ens_stream_t stream);
+int ens_grid_compact(float *grad, const int32_t *flags, const int32_t *pos, int64_t n_vox, float *compact, int64_t capacity,
+                     int to_compact, int32_t *overflow, ens_stream_t stream);
+
 /* Adam over many small tensors in ONE launch: the other parameter groups of the mapper's optimizer (decoder weights,
  * camera tensors; src/Mapper.py:396-423, :625) and the tracker's camera tensor (src/Tracker.py:335-342).  Same
  * arithmetic as ens_grid_adam_step.  params_host / grads_host / sizes_host / groups_host: host arrays of n_tensors device

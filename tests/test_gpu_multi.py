@@ -78,6 +78,22 @@ def _worker(rank, world, port, out):
         whole = grads(0, n, False)
         worst = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(part, whole))
         res["grad_rel"] = worst
+        # the same with native-layout grids and the touched-voxel all-reduce (sharding.SparseGradAllReduce)
+        from evennicer_slam_b200.scene import as_native_layout
+        from evennicer_slam_b200.functional import render_batch_ray, depth_batch_max
+        cn = {k: as_native_layout(v.clone()).requires_grad_(True) for k, v in c.items()}
+        keys = ["grid_middle", "grid_fine", "grid_color"]
+        ar = sharding.SparseGradAllReduce([cn[k] for k in keys], capacity_frac=0.9)
+        for p in decoders.parameters():
+            p.grad = None
+        setup = renderer._setup("color", decoders, dev)
+        d, u, col = render_batch_ray(setup, cn, decoders, rays_d[lo:hi], rays_o[lo:hi], sd[lo:hi], depth_max=depth_batch_max(sd.contiguous()))
+        (torch.abs(sd[lo:hi] - d).sum() + 0.2 * torch.abs(col).sum()).backward()
+        ps = [p for p in decoders.parameters() if p.grad is not None]
+        ar([cn[k].grad for k in keys], [p.grad for p in ps])
+        got = [cn[k].grad for k in keys] + [p.grad for p in ps]
+        res["sparse_rel"] = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(got, whole))
+        res["sparse_overflow"] = ar.overflowed()
         if rank == 0:
             out.put(res)
         dist.barrier()
@@ -100,3 +116,4 @@ def test_two_rank_sharding_matches_one_gpu():
         assert p.exitcode == 0
     assert res["frame"] and res["points"], res
     assert res["grad_rel"] < 1e-5, res
+    assert res["sparse_rel"] < 1e-5 and not res["sparse_overflow"], res
