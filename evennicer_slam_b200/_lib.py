@@ -49,6 +49,9 @@ class EnsGrads(C.Structure):
 _SIGNATURES = {
     "ens_version": (C.c_int, []),
     "ens_strerror": (C.c_char_p, [C.c_int]),
+    "ens_unet_input": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_void_p]),
+    "ens_unet_input_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ens_grid_touched": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ens_grid_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                    C.c_void_p]),

@@ -257,6 +257,14 @@ int ens_event_loss(const float *gt, const float *pred, int H, int W, int C, cons
                    const float *kernels1d_host, const float *kernel_weights_host, int n_kernels, float balancer,
                    double *loss_parts, float *g_pred, ens_stream_t stream);
 
+/* UNet input assembly of the event branch (the head of src/event_net.py:67-99, inference_event): img1 (previous GT colour,
+ * HWC float64 or float32, H1 x W1) and img2 (rendered colour, HWC float32, H2 x W2) -> out [6][h][w] float32 =
+ * cat(permute(img1), permute(img2)), each nearest-resized to h x w first when its size differs (torchvision Resize(NEAREST) =
+ * ATen upsample_nearest2d indexing).  ens_unet_input_bwd: g_out [6][h][w] -> g_img2 [H2][W2][3] (written). */
+int ens_unet_input(const void *img1, int img1_is_f64, int H1, int W1, const float *img2, int H2, int W2, int h, int w,
+                   float *out, ens_stream_t stream);
+int ens_unet_input_bwd(const float *g_out, int H2, int W2, int h, int w, float *g_img2, ens_stream_t stream);
+
 /* ---- RGB-D loss glue of the callers, value + gradients in one launch ----------------------
  * tracker = 0 (src/Mapper.py:553-562):  loss = sum_{gt_depth>0} |gt_depth - depth|  (+ w_color * sum |gt_color - color|
  *                                       when use_color: the mapper's colour stage; the colour term is NOT masked)
