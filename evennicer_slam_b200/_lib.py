@@ -49,6 +49,10 @@ class EnsGrads(C.Structure):
 _SIGNATURES = {
     "ens_version": (C.c_int, []),
     "ens_strerror": (C.c_char_p, [C.c_int]),
+    "ens_frustum_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "ens_frustum_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ens_keyframe_overlap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ens_unet_input": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p]),
     "ens_unet_input_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -139,5 +143,13 @@ def ptr(t):
 
 
 def cur_stream(device):
+    """Current stream of ``device`` for an ABI call.  The library launches on the calling thread's CURRENT device (one
+    process per GPU, ``torch.cuda.set_device(LOCAL_RANK)``): tensors on another device would fail inside the launch with an
+    opaque 'invalid resource handle', so say it here."""
     import torch
+    device = torch.device(device)
+    cur = torch.cuda.current_device()
+    if device.index is not None and device.index != cur:
+        raise RuntimeError(f"libens_render: tensors live on cuda:{device.index} but the current device is cuda:{cur}; "
+                           f"call torch.cuda.set_device({device.index}) or wrap the call in torch.cuda.device({device.index})")
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

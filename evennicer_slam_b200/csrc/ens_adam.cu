@@ -247,9 +247,7 @@ extern "C" int ens_grid_adam_step(const EnsAdamLevel *levels_host, int n_levels,
   if (!dyn) a.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
   a.clear_grad = clear_grad ? 1 : 0;
   // persistent grid: a multiple of the SM count, enough resident warps to cover HBM latency
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const long long need = (a.total_sel + (ADAM_THREADS / 8) * ADAM_UNROLL - 1) / ((ADAM_THREADS / 8) * ADAM_UNROLL);
   long long blocks = (long long)sms * 8;
   if (blocks > need) blocks = need;

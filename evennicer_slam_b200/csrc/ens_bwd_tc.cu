@@ -1260,9 +1260,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     const char *v = std::getenv("ENS_BWD_TC_DBG");          // tools/time_passes.py: device address of a long long[640]
     a.dbg = v ? reinterpret_cast<long long *>(std::strtoull(v, nullptr, 0)) : nullptr;
   }
-  int dev = 0, sms = 148;
-  ENS_CUDA_CALL(cudaGetDevice(&dev));
-  ENS_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = sm_count();
   // persistent CTAs per role, in proportion to the work of a tile (the FINE_CM role runs the hidden chain only)
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
   const int nroles = (wg && ndec > 1) ? 4 : ndec;

@@ -7,6 +7,17 @@ static thread_local char g_last_error[256] = "";
 void note_cuda_error(cudaError_t e, const char *file, int line) {
   std::snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s:%d)", cudaGetErrorName(e), cudaGetErrorString(e), file, line);
 }
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
 }  // namespace ens
 
 extern "C" const char *ens_last_error(void) { return ens::g_last_error; }

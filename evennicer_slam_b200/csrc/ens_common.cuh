@@ -7,7 +7,10 @@
 
 // Launch check: cudaGetLastError CLEARS a non-sticky error (bad launch configuration, too much shared memory), so a failed
 // launch does not poison every later call of this library or of PyTorch; the message is kept for ens_last_error().
-namespace ens { void note_cuda_error(cudaError_t e, const char *file, int line); }
+namespace ens {
+void note_cuda_error(cudaError_t e, const char *file, int line);
+int sm_count();   // SMs of the current device (cached per device; 148 on a B200), ens_capi.cu
+}
 #define ENS_CHECK_CUDA()                                   \
   do {                                                     \
     cudaError_t e__ = cudaGetLastError();                  \

@@ -270,9 +270,7 @@ static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_
   TcArgs a;
   a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0;
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int64_t pairs = ((n + 127) / 128 + 1) / 2;
   const unsigned g = (unsigned)(pairs < sms ? pairs : sms);
   if (f64) {
@@ -483,9 +481,7 @@ int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, c
   // the compositing kernel; otherwise one launch per decoder
   const float4 *planes = nullptr;
   int n_planes = 0;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
   const int64_t pairs = ((P + 127) / 128 + 1) / 2;
   if (ndec > 1 && pairs * ndec <= sms && use_tc_multi()) {

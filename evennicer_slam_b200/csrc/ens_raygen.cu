@@ -208,7 +208,7 @@ extern "C" int ens_rays_bwd(const float *pix_i, const float *pix_j, int64_t n, i
   if (n == 0) return ENS_OK;
   Cam cam{fx, fy, cx, cy};
   int64_t nb = (n + 255) / 256;
-  if (nb > 148 * 4) nb = 148 * 4;
+  if (nb > sm_count() * 4) nb = sm_count() * 4;
   rays_bwd_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(pix_i, pix_j, n, nW, cam, g_rays_o, g_rays_d, g_c2w);
   ENS_CHECK_CUDA();
   return ENS_OK;

@@ -977,7 +977,7 @@ static int launch_bwd_mma(BwdArgs &a, cudaStream_t s) {
     // small pose-only batches (tracking: 200 rays = 50 CTAs) leave most SMs idle and are bound by the latency of one CTA
     // walking its decoders in turn: give every decoder its own CTA while all of them still fit in one wave
     constexpr int ndec = (STAGE == ENS_STAGE_MIDDLE) ? 1 : (STAGE == ENS_STAGE_FINE ? 2 : 3);
-    if (ndec > 1 && (int64_t)g * ndec <= 296) {
+    if (ndec > 1 && (int64_t)g * ndec <= 2 * sm_count()) {
       a.dec_par = 1;
       gy = ndec;
       if (a.g_rays_o && cudaMemsetAsync(a.g_rays_o, 0, sizeof(float) * 3 * a.ra.R, s) != cudaSuccess) return ENS_ECUDA;
@@ -1033,7 +1033,7 @@ static int launch_bwd_mma_any(BwdArgs &a, bool wg, cudaStream_t s) {
   const size_t smem = (size_t)WGRAD_SMEM_FLOATS * 4;
   ENS_CUDA_CALL(cudaFuncSetAttribute(wgrad_split_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ndec = (STAGE == ENS_STAGE_MIDDLE) ? 1 : (STAGE == ENS_STAGE_FINE ? 2 : 3);
-  int64_t ctas = 296 / ndec;
+  int64_t ctas = 2 * sm_count() / ndec;
   if (ctas > tiles) ctas = tiles;
   wgrad_split_kernel<STAGE><<<dim3((unsigned)ctas, ndec), 256, smem, s>>>(wa);
   ENS_CHECK_CUDA();

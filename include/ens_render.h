@@ -257,6 +257,23 @@ int ens_event_loss(const float *gt, const float *pred, int H, int W, int C, cons
                    const float *kernels1d_host, const float *kernel_weights_host, int n_kernels, float balancer,
                    double *loss_parts, float *g_pred, ens_stream_t stream);
 
+/* ---- frustum feature selection and keyframe overlap of the mapper --------------------------------
+ * ens_frustum_mask replaces Mapper.get_mask_from_c2w (src/Mapper.py:115-186, numpy + cv2.remap on the host) for the
+ * middle / fine / colour grids: voxel centre (xs[ix], ys[iy], zs[iz]) is selected when it projects inside the image with
+ * 0 <= depth-along-axis <= bilinear(depth image) + 0.5 (zero depths read as the maximum over all voxels), or lies within
+ * 0.5 of the camera centre.  w2c_host = HOST float[12..16], rows 0..2 of inv(c2w) (the reference inverts on the host too);
+ * cam_centre_host = HOST float[3] = c2w[:3,3]; cam6_host = HOST double[6] = {H, W, fx, fy, cx, cy}; xs/ys/zs = DEVICE float
+ * coordinate axes (torch.linspace of the bound, :132-134); depth = DEVICE float32 [H][W]; mask = DEVICE uint8, [NZ][NY][NX]
+ * when mask_zyx != 0 (grid layout) else [NX][NY][NZ] (the reference's return value).  workspace: ens_frustum_workspace_bytes.
+ * ens_keyframe_overlap replaces the projection loop of keyframe_selection_overlap (:222-241): counts[k] = number of
+ * vertices [n][3] (DEVICE) that project more than `edge` pixels inside keyframe k's image, w2cs = DEVICE float [K][16]. */
+int64_t ens_frustum_workspace_bytes(int NX, int NY, int NZ);
+int ens_frustum_mask(const float *w2c_host, const float *cam_centre_host, const double *cam6_host, const float *xs,
+                     const float *ys, const float *zs, int NX, int NY, int NZ, const float *depth, int H, int W,
+                     int mask_zyx, uint8_t *mask, void *workspace, int64_t workspace_bytes, ens_stream_t stream);
+int ens_keyframe_overlap(const float *w2cs, int n_keyframes, const double *cam6_host, float edge, const float *vertices,
+                         int n_vertices, int *counts, ens_stream_t stream);
+
 /* UNet input assembly of the event branch (the head of src/event_net.py:67-99, inference_event): img1 (previous GT colour,
  * HWC float64 or float32, H1 x W1) and img2 (rendered colour, HWC float32, H2 x W2) -> out [6][h][w] float32 =
  * cat(permute(img1), permute(img2)), each nearest-resized to h x w first when its size differs (torchvision Resize(NEAREST) =
