@@ -543,6 +543,9 @@ __device__ __forceinline__ void issue_wgrad_part(uint32_t acc, uint32_t sA, uint
 }
 
 __device__ __forceinline__ void cta_sync288() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+// barrier 3: the four E warps arrive (g_u_i is in TMEM), the issuer warp waits
+__device__ __forceinline__ void cta_arrive_a() { asm volatile("bar.arrive 3, 160;" ::: "memory"); }
+__device__ __forceinline__ void cta_sync_a() { asm volatile("bar.sync 3, 160;" ::: "memory"); }
 
 template <int ROLE>
 __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_raw) {
@@ -644,19 +647,25 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
 #pragma unroll 1
       for (int ps = 0; ps < NPASS; ++ps) {
         const int i = pass_layer(ps);
-        tc_fence_before();
-        cta_sync288();
-        tc_fence_after();
+        // the data-gradient GEMM goes out as soon as the E warps have put g_u_i into TMEM (barrier 3); they stage the same
+        // rows for the weight-gradient pass while it runs
         if (i >= 1) {
+          cta_sync_a();
+          tc_fence_after();
           // [g_h | g_c | g_e] += g_u [WhT_i ; MT_{i-1} ; W3eT]
           if (!TAIL) issue_gemm<32, 32, 32>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(i), PB::TOT(), 1u);
           else if (i == 3) issue_gemm<32, 32, 160>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(3), PB::TOT(), 1u);
           else issue_gemm<32, 32, 64>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(i), PB::TOT(), 1u);
           umma_commit(&barD);
         } else if (i == 0 && TAIL) {
+          cta_sync_a();
+          tc_fence_after();
           issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(0), PB::TOT(), 1u);
           umma_commit(&barD);
         }
+        tc_fence_before();
+        cta_sync288();
+        tc_fence_after();
         issue_wgrad_loop(tb0 + TB_ACC + 32 * ps, sMBa, sNBa);
         umma_commit(&barW);
         __syncwarp();
@@ -691,19 +700,33 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
           for (int k = 0; k < 5; ++k) if (k == i) m = mw[k];
 #pragma unroll
           for (int k = 0; k < 32; ++k) g[k] = ((m >> k) & 1u) ? g[k] : 0.f;          // g_u_i
+          if (i >= 1 || TAIL) {                                                     // A operand of the data-gradient GEMM
+            tmem_st32_split(tb + TB_XH, tb + TB_XL, g);
+            tmem_st_done();
+            tc_fence_before();
+            cta_arrive_a();
+          }
+          ENS_DBG(ps, 1);
           const float bs = warp_colsum32(g);
 #pragma unroll
           for (int k = 0; k < 5; ++k) if (k == i) bhat[k] += bs;
-          if (i >= 1 || TAIL) tmem_st32_split(tb + TB_XH, tb + TB_XL, g);           // A operand of the data-gradient GEMM
-          ENS_DBG(ps, 1);
           if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
           ENS_DBG(ps, 2);
           stage_row(sNB, sNB + 4096, pl, g);
-          tmem_st_done();
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           ENS_DBG(ps, 3);
         } else {
+          // Fourier pass: the H warps fill one slot, these warps the other (pass 2: e1 -> slot B, 3: e2 -> slot A, 7: e2 -> slot B)
+          const int je = (ps == 2) ? 1 : 2;
+          const float *B = sw + PB::off_B();
+          float ve[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            ve[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * je + k], fmaf(p32[1], B[EMBP + 32 * je + k], p32[0] * B[32 * je + k])));
           if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+          if (ps == 3) stage_row(sMB, sMB + 2 * 4096, pl, ve);
+          else stage_row(sMB + 4096, sMB + 3 * 4096, pl, ve);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         first = false;
         tc_fence_before();
@@ -825,11 +848,10 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         if (TAIL) {
           // slot A <- r_{i-1} (blocks 4..1) or a Fourier chunk; slot B <- a Fourier chunk or the features again
           //   pass:    0   1   2      3      4   5   6    7
-          //   slot A:  r3  r2  e0     e2     r1  r0  e0   e1
-          //   slot B:  .   .   e1     c      .   .   .    e2
-          const int ja = (ps == 2 || ps == 6) ? 0 : (ps == 3 ? 2 : (ps == 7 ? 1 : -1));
-          const int jb = (ps == 2) ? 1 : (ps == 7 ? 2 : -1);
-          float va[32], vb[32];
+          //   slot A:  r3  r2  e0     e2*    r1  r0  e0   e1        (* = computed and staged by the E warps, idle in those passes)
+          //   slot B:  .   .   e1*    c      .   .   .    e2*
+          const int ja = (ps == 2 || ps == 6) ? 0 : (ps == 7 ? 1 : -1);
+          float va[32];
           if (ja >= 0) {
 #pragma unroll
             for (int k = 0; k < 32; ++k)
@@ -838,22 +860,14 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
 #pragma unroll
             for (int k = 0; k < 32; ++k) va[k] = rn[k];
           }
-          if (jb >= 0) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              vb[k] = fast_sin(fmaf(p32[2], B[2 * EMBP + 32 * jb + k], fmaf(p32[1], B[EMBP + 32 * jb + k], p32[0] * B[32 * jb + k])));
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) vb[k] = c[k];
-          }
           // the next main pass's slot A (r_{i-2}) is fetched while this pass's MMAs run
           const int nxt = (ps + 1 < NPASS) ? pass_layer(ps + 1) : -1;
           if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
           ENS_DBG(ps, 1);
           if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }
           ENS_DBG(ps, 2);
-          stage_row(sMB, sMB + 2 * 4096, pl, va);
-          if (jb >= 0 || ps == 3) stage_row(sMB + 4096, sMB + 3 * 4096, pl, vb);
+          if (ps == 3) stage_row(sMB + 4096, sMB + 3 * 4096, pl, c);
+          else stage_row(sMB, sMB + 2 * 4096, pl, va);
           ENS_DBG(ps, 3);
         } else {
           if (!waited) { mbar_wait(&barW, pw); pw ^= 1; }

@@ -11,11 +11,12 @@ nrays = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 scene = cases.room0_scene()
 decoders, c, renderer, cfg = harness.build(scene, dev, requires_grad=True)
 ro, rd, sd, sc = mapping_batch(scene, nrays, dev)
-cg = {k: v.clone().requires_grad_(True) for k, v in c.items()}
+GRID = 'nogrid' not in sys.argv; RAYS = 'norays' not in sys.argv
+cg = {k: v.clone().requires_grad_(GRID) for k, v in c.items()}
 dbg = torch.zeros(4 * 10 * 2 * 8, dtype=torch.int64, device=dev)
 for it in range(4):
     if it == 3: os.environ['ENS_BWD_TC_DBG'] = str(dbg.data_ptr())
-    ro_ = ro.clone().requires_grad_(True); rd_ = rd.clone().requires_grad_(True)
+    ro_ = ro.clone().requires_grad_(RAYS); rd_ = rd.clone().requires_grad_(RAYS)
     d, u, col = renderer.render_batch_ray(cg, decoders, rd_, ro_, dev, 'color', gt_depth=sd)
     loss = torch.where(sd > 0, torch.abs(sd - d), 0.0).sum() + 0.2 * torch.abs(sc - col).sum()
     loss.backward()
