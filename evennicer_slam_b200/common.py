@@ -38,6 +38,25 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
     return rays_o, rays_d, sample_depth, sample_color
 
 
+def get_samples_event(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, event1, event2, device):
+    """Get n rays from the image region H0..H1, W0..W1 together with the two event images' samples (common.py:178-187).
+    One draw (common.py:116) serves rays, depth, colour and both event images, as in the reference."""
+    indices = torch.randint((H1 - H0) * (W1 - W0), (n,), device=device)     # common.py:116 (the clamp at :117 is a no-op)
+    c2w = _c2w_dev(c2w, device)
+    ext = _ext.module() if (_ext.ENABLED and not TIMER.enabled) else None
+    if ext is not None:
+        rays_o, rays_d, sample_depth, sample_color = ext.sample_rays(
+            c2w, indices, depth, color, [int(H0), int(H1), int(W0), int(W1)],
+            [float(H), float(W), float(fx), float(fy), float(cx), float(cy)])
+    else:
+        rays_o, rays_d, sample_depth, sample_color = _SampleRays.apply(
+            c2w, indices, (int(H0), int(H1), int(W0), int(W1)),
+            (int(H), int(W), float(fx), float(fy), float(cx), float(cy)), depth, color)
+    sample_event1 = event1[H0:H1, W0:W1].reshape(-1, 2)[indices]            # common.py:122-127
+    sample_event2 = event2[H0:H1, W0:W1].reshape(-1, 2)[indices]
+    return rays_o, rays_d, sample_depth, sample_color, sample_event1, sample_event2
+
+
 def get_rays_from_uv(i, j, c2w, H, W, fx, fy, cx, cy, device):
     """Rays of arbitrary pixel coordinates (common.py:74-89): the lattice kernel in pairs mode."""
     c2w = _c2w_dev(c2w, device)

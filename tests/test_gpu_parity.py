@@ -83,6 +83,33 @@ def test_get_samples_bit_exact(tiny):
     print("eager-CUDA rays identical:", bool(torch.equal(rd, rd_eager)), "max ulp-ish diff", float((rd - rd_eager).abs().max()))
 
 
+def test_get_samples_event_shares_one_draw(tiny):
+    """common.py:178-187: rays, depth, colour and both event images come from ONE torch.randint draw."""
+    from evennicer_slam_b200 import common
+    scene, g = tiny["scene"], tiny["g"]
+    cam = scene.cam
+    c2w = torch.from_numpy(g["color.d.c2w"]).to(DEV)
+    depth = torch.from_numpy(tiny["depth"]).to(DEV)
+    color = torch.from_numpy(tiny["color"]).to(DEV)
+    gen = torch.Generator(device=DEV); gen.manual_seed(1)
+    ev1 = torch.randn(cam.H, cam.W, 2, device=DEV, generator=gen)
+    ev2 = torch.randn(cam.H, cam.W, 2, device=DEV, generator=gen)
+    H0, H1, W0, W1 = 2, cam.H - 3, 1, cam.W - 2
+    n = 77
+    torch.manual_seed(9)
+    idx = torch.randint((H1 - H0) * (W1 - W0), (n,), device=DEV).cpu().numpy()
+    torch.manual_seed(9)
+    ro, rd, sd, scol, se1, se2 = common.get_samples_event(H0, H1, W0, W1, n, cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy,
+                                                          c2w, depth, color, ev1, ev2, DEV)
+    i, j, d_ref, c_ref = orc.select_pixels(idx, H0, H1, W0, W1, tiny["depth"], tiny["color"])
+    ro_ref, rd_ref = orc.rays_from_uv(i, j, g["color.d.c2w"], cam.fx, cam.fy, cam.cx, cam.cy)
+    assert np.array_equal(rd.cpu().numpy(), rd_ref) and np.array_equal(ro.cpu().numpy(), ro_ref)
+    assert np.array_equal(sd.cpu().numpy(), d_ref) and np.array_equal(scol.cpu().numpy(), c_ref)
+    e1 = ev1.cpu().numpy()[H0:H1, W0:W1].reshape(-1, 2)[idx]
+    e2 = ev2.cpu().numpy()[H0:H1, W0:W1].reshape(-1, 2)[idx]
+    assert np.array_equal(se1.cpu().numpy(), e1) and np.array_equal(se2.cpu().numpy(), e2)
+
+
 def test_get_samples_indices_match_cpu_golden_when_generators_agree(tiny):
     """torch's CPU and CUDA generators differ, so golden indices (CPU) are checked by feeding them
     through the kernel rather than by re-drawing."""
