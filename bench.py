@@ -663,7 +663,10 @@ def load_traffic():
     if os.path.exists(path):
         try:
             with open(path) as f:
-                return json.load(f).get("render_bwd_dram_bytes_per_launch")
+                t = json.load(f)
+                from evennicer_slam_b200 import functional
+                # the round-1 capture belongs to the mma.sync backward (ENS_MAP_TC=0), the round-2 one to the tcgen05 backward
+                return t.get("render_bwd_dram_bytes_per_launch" if functional.TC_MAP else "r01_render_bwd_dram_bytes_per_launch")
         except Exception:
             return None
     return None
