@@ -794,8 +794,14 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
     } else {
       // ================================ H warps ================================
       float c[32], rn[32];
+      if (TAIL) load_row32(rbase + 4 * 4096, rn);                 // r_4: in flight during the gather
+      const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
+      if (!first) { mbar_wait(&barW, pw); pw ^= 1; }              // the previous tile's last pass: the M-side blocks are free
+      // features straight into slot B: gather_warp's tile layout IS the MN-major swizzle (32-byte chunk ^ (row & 3))
+      float *tileB = sMB + 4096 + w4 * 1024;
+      __syncwarp();
+      gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
       if (TAIL) {
-        load_row32(rbase + 4 * 4096, rn);                         // r_4
         // output layer sums: sum g_out[o] r_4[k], sum g_out[o]
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
@@ -808,15 +814,9 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
           for (int off = 16; off > 0; off >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, off);
           dbo[o] += sg;
         }
-        load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0 (in flight during the gather)
+        load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0 (in flight during the sums below)
       }
-      const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
-      if (!first) { mbar_wait(&barW, pw); pw ^= 1; }              // the previous tile's last pass: the M-side blocks are free
       {
-        // features straight into slot B: gather_warp's tile layout IS the MN-major swizzle (32-byte chunk ^ (row & 3))
-        float *tileB = sMB + 4096 + w4 * 1024;
-        __syncwarp();
-        gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
         float *lrow = sMB + 3 * 4096 + w4 * 1024 + lane * 32;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1302,7 +1302,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     u.raw = raw;
     for (int l = 0; l < 4; ++l) { u.w[l] = b.sc.w[l]; u.gdec[l] = b.gdec[l]; }
     ENS_CUDA_CALL(cudaFuncSetAttribute(unfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UNFOLD_SMEM_FLOATS * 4));
-    unfold_kernel<<<dim3(ndec, 6), 512, UNFOLD_SMEM_FLOATS * 4, s>>>(u, stage);
+    unfold_kernel<<<dim3(ndec, 32), 512, UNFOLD_SMEM_FLOATS * 4, s>>>(u, stage);   // 96 CTAs: the work is index arithmetic, not bytes
     ENS_CHECK_CUDA();
   }
   if (want_rays) {
