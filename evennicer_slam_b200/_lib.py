@@ -19,7 +19,7 @@ STAGE_LEVELS = {"coarse": ("coarse",), "middle": ("middle",), "fine": ("middle",
                 "color": ("middle", "fine", "color")}
 
 ENS_OK = 0
-ABI_VERSION = 5            # include/ens_render.h: ENS_ABI_VERSION
+ABI_VERSION = 6            # include/ens_render.h: ENS_ABI_VERSION
 
 
 class EnsScene(C.Structure):

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ENS_ABI_VERSION 5
+#define ENS_ABI_VERSION 6
 
 typedef void *ens_stream_t; /* cudaStream_t */
 
