@@ -39,7 +39,7 @@ def tiny():
 def test_library_loads_and_reports_version():
     from evennicer_slam_b200 import _lib
     L = _lib.lib()
-    assert L.ens_version() == 5
+    assert L.ens_version() == _lib.ABI_VERSION
     assert L.ens_packed_decoder_floats(2) == 21028 + 22244 + 16800 + 37700 + 29216 and L.ens_decoder_grad_floats(3) == 15899
 
 
