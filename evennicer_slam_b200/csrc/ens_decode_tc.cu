@@ -34,6 +34,7 @@ struct TcArgs {
                           // [n_tiles32][5][32], word (tile, i, j) = point 32 tile + j, bit k = unit k of block i active
   float *rsave;           // optional: this decoder's relu outputs r_0..r_4 = relu(u_i), [n_tiles128][5][128][32] -- what the
                           // tcgen05 backward (ens_bwd_tc.cu) needs for the weight gradients (saved kind 3)
+  int nctas;              // CTAs that walk this decoder's tiles (0: gridDim.x)
 };
 
 // Two 128-point tiles are in flight per CTA: tile group 0 = warps 0-3, group 1 = warps 4-7; each owns 256 TMEM columns,
@@ -85,7 +86,8 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
   uint32_t parity = 0;
 
   const int64_t n_tiles = (a.n + 127) / 128;
-  for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+  const int64_t tile_stride = (int64_t)(a.nctas > 0 ? a.nctas : (int)gridDim.x) * 2;
+  for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < n_tiles; tile += tile_stride) {
     const int64_t pt = tile * 128 + gt;
     const bool valid = pt < a.n;
     float pn[3], p32[3];
@@ -240,14 +242,17 @@ __global__ void __launch_bounds__(256, 1) decode_tc_kernel(TcArgs a) {
   decode_tc_body<LEVEL, CD, NO, F64>(a, smem);
 }
 
-// All decoders of a stage in ONE launch, blockIdx.y = decoder, each writing its own output plane (TcArgs::separate):
-// for small batches (tracking: 9 600 points = 38 CTAs per decoder) three back-to-back launches are three times the
-// latency of one tile chain; side by side they still fit on the 148 SMs.
+// All decoders of a stage in ONE launch, blockIdx.y = decoder, each writing its own output plane (TcArgs::separate).
+// Small batches (tracking: 9 600 points = 38 CTAs per decoder): three back-to-back launches are three times the latency of
+// one tile chain; side by side they still fit on the 148 SMs.  Larger batches (mapping: 375 tiles per decoder): the SMs are
+// dealt to the decoders in proportion to their cost and every CTA walks its decoder's tiles -- 1125 tiles over 147 x 2 tile
+// groups is 4 rounds, where three launches of 375 tiles over 296 groups are 3 x 2.
 struct TcMultiArgs {
   TcArgs base;
   float *out[3];
   uint32_t *msave[3];
   float *rsave[3];
+  int ctas[3];
 };
 
 template <int STAGE>
@@ -255,6 +260,8 @@ __global__ void __launch_bounds__(256, 1) decode_tc_multi_kernel(TcMultiArgs m) 
   extern __shared__ __align__(128) float smem[];
   TcArgs a = m.base;
   const int d = blockIdx.y;
+  if ((int)blockIdx.x >= m.ctas[d]) return;
+  a.nctas = m.ctas[d];
   a.out4 = m.out[d];
   a.msave = m.msave[d];
   a.rsave = m.rsave[d];
@@ -268,7 +275,7 @@ template <int LEVEL, int CD, int NO>
 static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s,
                             uint32_t *msave = nullptr, float *rsave = nullptr) {
   TcArgs a;
-  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0; a.nctas = 0;
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   const int sms = sm_count();
   const int64_t pairs = ((n + 127) / 128 + 1) / 2;
@@ -451,6 +458,7 @@ static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P
   m.base.sc = a.sc; m.base.pts = pts; m.base.n = P; m.base.out4 = nullptr; m.base.apply_mask = 0; m.base.msave = nullptr;
   m.base.rsave = nullptr;
   m.base.separate = 1;
+  m.base.nctas = 0;
   const int64_t rstride = ((P + 127) / 128) * TC_RSAVE_TILE_FLOATS;
   for (int d = 0; d < 3; ++d) {
     m.out[d] = planes + (int64_t)d * P * 4;
@@ -460,7 +468,24 @@ static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P
   const size_t smem = (size_t)(MlpPackTC<64>::total() + 8 * 1024) * 4;       // the fine decoder's blob is the largest
   ENS_CUDA_CALL(cudaFuncSetAttribute(decode_tc_multi_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t pairs = ((P + 127) / 128 + 1) / 2;
-  decode_tc_multi_kernel<STAGE><<<dim3((unsigned)pairs, ndec), 256, smem, s>>>(m);
+  int gx = 0;
+  if (pairs * ndec <= sms) {
+    for (int d = 0; d < 3; ++d) m.ctas[d] = d < ndec ? (int)pairs : 0;
+    gx = (int)pairs;
+  } else {
+    // persistent: SMs in proportion to the decoders' cost per tile (ncu, 1000-ray colour-stage forward: 38.8 / 50.8 / 41.5 us)
+    const double cost[3] = {1.0, 1.31, 1.07};
+    double tot = 0.0;
+    for (int d = 0; d < ndec; ++d) tot += cost[d];
+    for (int d = 0; d < 3; ++d) {
+      int64_t n = d < ndec ? (int64_t)(sms * cost[d] / tot) : 0;
+      if (d < ndec && n < 1) n = 1;
+      if (n > pairs) n = pairs;
+      m.ctas[d] = (int)n;
+      if ((int)n > gx) gx = (int)n;
+    }
+  }
+  decode_tc_multi_kernel<STAGE><<<dim3((unsigned)gx, ndec), 256, smem, s>>>(m);
   ENS_CHECK_CUDA();
   return ENS_OK;
 }
@@ -477,14 +502,16 @@ int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, c
   const unsigned g = (unsigned)((a.ra.R + a.ra.rpc - 1) / a.ra.rpc);
   place_kernel<<<g, NT_MMA, 0, s>>>(a.sc, a.ra, z, pts);
   ENS_CHECK_CUDA();
-  // small batch: every decoder of the stage side by side in one launch (all CTAs resident at once), outputs combined by
-  // the compositing kernel; otherwise one launch per decoder
+  // every decoder of the stage side by side in one launch (small batch: all tiles resident at once; otherwise persistent
+  // CTAs dealt to the decoders by cost), outputs combined by the compositing kernel; ENS_TC_MULTI=0: one launch per decoder
   const float4 *planes = nullptr;
   int n_planes = 0;
   const int sms = sm_count();
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
   const int64_t pairs = ((P + 127) / 128 + 1) / 2;
-  if (ndec > 1 && pairs * ndec <= sms && use_tc_multi()) {
+  // (measured: one launch wins up to a few tile rounds per SM -- 0.153 -> 0.128 ms at 1000 rays -- and loses 3-10 % to the
+  // per-decoder launches from 16 k rays on, where the static split of the SMs matters more than the round quantisation)
+  if (ndec > 1 && pairs * ndec <= 8 * (int64_t)sms && use_tc_multi()) {
     float *pl = reinterpret_cast<float *>(base + P * 48);
     const int rc = stage == ENS_STAGE_FINE ? launch_decode_tc_multi<ENS_STAGE_FINE>(a, pts, P, pl, s, sms)
                                            : launch_decode_tc_multi<ENS_STAGE_COLOR>(a, pts, P, pl, s, sms);
