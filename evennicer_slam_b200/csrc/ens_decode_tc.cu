@@ -35,6 +35,7 @@ struct TcArgs {
   float *rsave;           // optional: this decoder's relu outputs r_0..r_4 = relu(u_i), [n_tiles128][5][128][32] -- what the
                           // tcgen05 backward (ens_bwd_tc.cu) needs for the weight gradients (saved kind 3)
   int nctas;              // CTAs that walk this decoder's tiles (0: gridDim.x)
+  int nopipe;             // ENS_TC_PIPE=0: gather every tile up front instead of during the previous tile's round trips (A/B)
 };
 
 // Two 128-point tiles are in flight per CTA: tile group 0 = warps 0-3, group 1 = warps 4-7; each owns 256 TMEM columns,
@@ -86,6 +87,7 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
   uint32_t parity = 0;
 
   const int64_t n_tiles = (a.n + 127) / 128;
+  bool have_pref = false;                             // the staging tile already holds this tile's features (level LEVEL)
   const int64_t tile_stride = (int64_t)(a.nctas > 0 ? a.nctas : (int)gridDim.x) * 2;
   for (int64_t tile = (int64_t)blockIdx.x * 2 + grp; tile < n_tiles; tile += tile_stride) {
     const int64_t pt = tile * 128 + gt;
@@ -111,12 +113,16 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
     // Warp-cooperative gather (8 lanes per 128-byte voxel line, as in the mma kernels: a thread-per-point gather costs
     // 8x the L1 wavefronts and was the kernel's top stall) into the warp's swizzled [32][32] staging tile; each thread
     // then reads back its own row.
+    // The first half (the decoder's own level) of every tile but a CTA's first was gathered during the previous tile's
+    // MMA round trips, one group of four points per round trip (gather_warp_step): its L2 latency hides behind the waits.
 #pragma unroll
     for (int half = 0; half < CD / 32; ++half) {      // fine decoder: [fine | middle] concat (decoder.py:182-187)
       const int lv = (half == 0) ? LEVEL : ENS_LEVEL_MIDDLE;
-      const Vox v = make_vox(pn, a.sc.dims[lv]);
       __syncwarp();
-      gather_warp<32>(a.sc.grid[lv], a.sc.dims[lv], v, stile, 0);
+      if (half > 0 || !have_pref) {
+        const Vox v = make_vox(pn, a.sc.dims[lv]);
+        gather_warp<32>(a.sc.grid[lv], a.sc.dims[lv], v, stile, 0);
+      }
       float f[32];
       const int lane = tid & 31;
 #pragma unroll
@@ -126,6 +132,26 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
       }
       tmem_st32_split(tb + TC_FH + 32 * half, tb + TC_FL + 32 * half, f);
     }
+    // ---- the next tile of this group: its voxel, for the gather steps below ----
+    const int64_t tile_n = tile + tile_stride;
+    const bool has_next = tile_n < n_tiles && !a.nopipe;
+    Vox vn = make_vox(pn, a.sc.dims[LEVEL]);
+    if (has_next) {
+      const int64_t ptn = tile_n * 128 + gt;
+      float pnn[3];
+      if (F64) {
+        double p[3] = {0.0, 0.0, 0.0};
+        if (ptn < a.n) { const double *pp = (const double *)a.pts + ptn * 3; p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2]; }
+        normalize64(p, a.sc.lo, a.sc.hi, pnn);
+      } else {
+        float q[3] = {0.f, 0.f, 0.f};
+        if (ptn < a.n) { const float *pp = (const float *)a.pts + ptn * 3; q[0] = pp[0]; q[1] = pp[1]; q[2] = pp[2]; }
+        normalize32(q, a.sc.lo, a.sc.hi, pnn);
+      }
+      vn = make_vox(pnn, a.sc.dims[LEVEL]);
+    }
+    int gstep = 0;
+    __syncwarp();                                      // every lane has read its row of the staging tile
     // ---- embedding chunks: D += e W0^T, D3 += e W3e^T ----
 #pragma unroll 1
     for (int jc = 0; jc < 3; ++jc) {
@@ -150,6 +176,7 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
         umma_commit(bar);
         __syncwarp();
       }
+      if (has_next) { gather_warp_step<32>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], vn, stile, 0, gstep); ++gstep; }
     }
     // ---- blocks 0..4:  r_i = relu(u_i + b'_i);  u_{i+1} = W_{i+1} r_i + M_i c ----
     float r[32];
@@ -186,8 +213,14 @@ __device__ __forceinline__ void decode_tc_body(const TcArgs &a, float *smem) {
           umma_commit(bar);
           __syncwarp();
         }
+        if (has_next) { gather_warp_step<32>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], vn, stile, 0, gstep); ++gstep; }
       }
     }
+    if (has_next) {                                    // seven round trips, eight groups: the last one here
+      gather_warp_step<32>(a.sc.grid[LEVEL], a.sc.dims[LEVEL], vn, stile, 0, gstep);
+      __syncwarp();
+    }
+    have_pref = has_next;
     // ---- output layer (FMA pipe): out = Wo r_4 + Mo c + bo' ----
     float o[NO];
 #pragma unroll
@@ -271,11 +304,16 @@ __global__ void __launch_bounds__(256, 1) decode_tc_multi_kernel(TcMultiArgs m) 
   else if (STAGE == ENS_STAGE_COLOR) decode_tc_body<ENS_LEVEL_COLOR, 32, 4, true>(a, smem);
 }
 
+static int tc_nopipe() {
+  const char *v = std::getenv("ENS_TC_PIPE");
+  return (v && v[0] == '0') ? 1 : 0;
+}
+
 template <int LEVEL, int CD, int NO>
 static int launch_decode_tc(const DevScene &sc, const void *pts, int f64, int64_t n, int apply_mask, float *out4, cudaStream_t s,
                             uint32_t *msave = nullptr, float *rsave = nullptr) {
   TcArgs a;
-  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0; a.nctas = 0;
+  a.sc = sc; a.pts = pts; a.n = n; a.out4 = out4; a.apply_mask = apply_mask; a.msave = msave; a.rsave = rsave; a.separate = 0; a.nctas = 0; a.nopipe = tc_nopipe();
   const size_t smem = (size_t)(MlpPackTC<CD>::total() + 8 * 1024) * 4;      // blob + one staging tile per warp
   const int sms = sm_count();
   const int64_t pairs = ((n + 127) / 128 + 1) / 2;
@@ -459,6 +497,7 @@ static int launch_decode_tc_multi(const FwdArgs &a, const double *pts, int64_t P
   m.base.rsave = nullptr;
   m.base.separate = 1;
   m.base.nctas = 0;
+  m.base.nopipe = tc_nopipe();
   const int64_t rstride = ((P + 127) / 128) * TC_RSAVE_TILE_FLOATS;
   for (int d = 0; d < 3; ++d) {
     m.out[d] = planes + (int64_t)d * P * 4;

@@ -342,6 +342,41 @@ __device__ __forceinline__ void gather_warp(const float *__restrict__ grid, cons
   __syncwarp();
 }
 
+// one group of four points (grp = 0..7) of gather_warp: callers that have latency to hide elsewhere (the tcgen05 decode walks
+// its MMA round trips) run the eight groups of the NEXT tile one at a time in between
+template <int RS>
+__device__ __forceinline__ void gather_warp_step(const float *__restrict__ grid, const int dims[3], const Vox &v,
+                                                 float *__restrict__ crow, int c0, int grp) {
+  const int lane = threadIdx.x & 31;
+  const int X = dims[2], Y = dims[1], Z = dims[0];
+  // owner-side packing: base element offset of corner 0, per-axis steps (0 if the +1 neighbour is out of range)
+  const int base = ((v.z0 * Y + v.y0) * X + v.x0) * C;
+  const bool okx = v.x0 + 1 < X, oky = v.y0 + 1 < Y, okz = v.z0 + 1 < Z;
+  const float wx1 = okx ? v.fx : 0.f, wy1 = oky ? v.fy : 0.f, wz1 = okz ? v.fz : 0.f;
+  const int cq = lane & 7, pp = lane >> 3;
+  const int sx = C, sy = X * C, sz = X * Y * C;
+  const int src = 4 * grp + pp;
+  const int b = __shfl_sync(0xffffffffu, base, src);
+  const float fx1 = __shfl_sync(0xffffffffu, wx1, src), fx0 = __shfl_sync(0xffffffffu, v.gx, src);
+  const float fy1 = __shfl_sync(0xffffffffu, wy1, src), fy0 = __shfl_sync(0xffffffffu, v.gy, src);
+  const float fz1 = __shfl_sync(0xffffffffu, wz1, src), fz0 = __shfl_sync(0xffffffffu, v.gz, src);
+  const unsigned okb = __shfl_sync(0xffffffffu, (unsigned)okx | ((unsigned)oky << 1) | ((unsigned)okz << 2), src);
+  const int ox = (okb & 1u) ? sx : 0, oy = (okb & 2u) ? sy : 0, oz = (okb & 4u) ? sz : 0;
+  const float *p = grid + b + 4 * cq;
+  float4 a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    a[c] = __ldg(reinterpret_cast<const float4 *>(p + ((c & 1) ? ox : 0) + ((c & 2) ? oy : 0) + ((c & 4) ? oz : 0)));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    // ATen order of the product: (wx * wy) * wz
+    const float w = __fmul_rn(__fmul_rn((c & 1) ? fx1 : fx0, (c & 2) ? fy1 : fy0), (c & 4) ? fz1 : fz0);
+    r.x = fmaf(a[c].x, w, r.x); r.y = fmaf(a[c].y, w, r.y); r.z = fmaf(a[c].z, w, r.z); r.w = fmaf(a[c].w, w, r.w);
+  }
+  *reinterpret_cast<float4 *>(crow + src * RS + ((c0 + 4 * cq) ^ ((src & 3) << 3))) = r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // trilinear backward for the warp's 32 points.  crow: the warp's feature-tile rows; columns 0..31 hold the
 // feature gradient g_c (swizzled) -- written by store_tile just before.  8 lanes per point.
