@@ -63,7 +63,7 @@ struct BwdTcArgs {
 // TMEM columns
 constexpr int TB_XH = 0, TB_XL = 32, TB_DH = 64, TB_DC = 96, TB_DE = 128, TB_ACC = 224;
 
-__device__ __forceinline__ void cta_sync128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void grp_sync128(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory"); }
 
 // column sums over the warp: lane k gets sum_lanes v[k]  (reduce-scatter: 16 + 8 + 4 + 2 + 1 shuffles)
 __device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {
@@ -135,29 +135,36 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
 
   // ---- shared memory: [M-side 4 blocks | N-side 2 blocks] (WG) or one staging block, then the weight blob ----
   float *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) / 4;    // swizzle atoms need SHARED-space alignment
-  float *sMB = base;                                   // hiA, hiB, loA, loB   (hiA doubles as the warps' 32x32 staging tiles)
-  float *sNB = base + (WG ? 16384 : 4096);             // g_hi, g_lo
+  // Pose-only form (!WG): TWO 128-point tiles in flight per CTA, as in the decode kernel -- tile group 0 = warps 0-3, group
+  // 1 = warps 4-7, each with its own 256 TMEM columns, staging block, mbarrier and named barrier; one group's tail and
+  // epilogues overlap the other's MMAs (4 warps per SM could not hide anything).
+  const int tid_all = threadIdx.x;
+  const int grp = WG ? 0 : (tid_all >> 7);
+  float *sMB = base + (WG ? 0 : grp * 4096);           // hiA, hiB, loA, loB   (hiA doubles as the warps' 32x32 staging tiles)
+  float *sNB = base + (WG ? 16384 : 8192);             // g_hi, g_lo (WG only)
   float *sw = sNB + (WG ? 8192 : 0);
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float4 sP[128];                           // p.float() of the tile's points (dB reduction)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ float4 sP[128];                           // p.float() of the tile's points (dB reduction, WG only)
+  const int tid = tid_all & 127, warp = tid >> 5, lane = tid & 31;      // thread / warp WITHIN the tile group
+  uint64_t *const barp = &bars[grp];
   float *stile = sMB + warp * 1024;
-  constexpr uint32_t TCOLS = WG ? 512u : 256u;
+  constexpr uint32_t TCOLS = 512u;
 
   {
     const float *gw = a.sc.w[LEVEL] + off_tcb<CD>();
     const uint32_t s0 = smem_u32(sw);
-    for (int i = tid; i < PB::total() / 4; i += 128)
+    for (int i = tid_all; i < PB::total() / 4; i += (int)blockDim.x)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + i * 16), "l"(gw + i * 4) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+  if (tid_all == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if ((tid_all >> 5) == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -165,7 +172,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb0 = tmem_base_s;
+  const uint32_t tb0 = tmem_base_s + (WG ? 0u : (uint32_t)(256 * grp));
   const uint32_t tb = tb0 + ((uint32_t)(32 * warp) << 16);
   const uint32_t swb = smem_u32(sw), sMBa = smem_u32(sMB), sNBa = smem_u32(sNB);
   uint32_t parity = 0;
@@ -187,7 +194,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
     }
     tmem_st_done();
     tc_fence_before();
-    cta_sync128();
+    grp_sync128(grp);
     tc_fence_after();
   }
 
@@ -200,7 +207,8 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
 
   const bool want_rays = TAIL && a.gp != nullptr;
   const int nctas = a.ctas[ROLE];
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+  constexpr int NGRP = WG ? 1 : 2;
+  for (int64_t tile = (int64_t)blockIdx.x * NGRP + grp; tile < a.n_tiles; tile += (int64_t)nctas * NGRP) {
     const int64_t pt = tile * 128 + tid;
     const bool valid = pt < a.P;
     double p[3] = {0.0, 0.0, 0.0};
@@ -305,7 +313,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
       tmem_st_done();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
-      cta_sync128();
+      grp_sync128(grp);
       if (warp == 0) {
         tc_fence_after();
         if (i >= 1) {
@@ -320,10 +328,10 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
           const int acc = (ROLE == ROLE_FINE_CM) ? (4 - i) : (i == 4 ? 0 : (i == 3 ? 1 : (i == 2 ? 4 : (i == 1 ? 5 : 6))));
           issue_wgrad(tb0 + TB_ACC + 32 * acc, sMBa, sNBa);
         }
-        umma_commit(&bar);
+        umma_commit(barp);
         __syncwarp();
       }
-      mbar_wait(&bar, parity); parity ^= 1;
+      mbar_wait(barp, parity); parity ^= 1;
       tc_fence_after();
       if (i >= 1) tmem_ld32(tb + TB_DH, g);
       // ---- the Fourier-feature operands of blocks 3 and 0:  E_i = sum g_u_i^T e ----
@@ -341,14 +349,14 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
-        cta_sync128();
+        grp_sync128(grp);
         if (warp == 0) {
           tc_fence_after();
           issue_wgrad(tb0 + TB_ACC + 32 * (i == 3 ? 2 : 7), sMBa, sNBa);
-          umma_commit(&bar);
+          umma_commit(barp);
           __syncwarp();
         }
-        mbar_wait(&bar, parity); parity ^= 1;
+        mbar_wait(barp, parity); parity ^= 1;
         tc_fence_after();
         if (i == 3) {       // pass 2: [e2 | c] -- slot B gets the features back for blocks 2, 1, 0
 #pragma unroll
@@ -358,14 +366,14 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
           stage_row(sMB + 4096, sMB + 3 * 4096, tid, c);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           tc_fence_before();
-          cta_sync128();
+          grp_sync128(grp);
           if (warp == 0) {
             tc_fence_after();
             issue_wgrad(tb0 + TB_ACC + 32 * 3, sMBa, sNBa);
-            umma_commit(&bar);
+            umma_commit(barp);
             __syncwarp();
           }
-          mbar_wait(&bar, parity); parity ^= 1;
+          mbar_wait(barp, parity); parity ^= 1;
           tc_fence_after();
         }
       }
@@ -446,7 +454,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
     }
     // the next tile's staging / tcgen05.st must not overtake this tile's TMEM loads and shared-tile reads
     tc_fence_before();
-    cta_sync128();
+    grp_sync128(grp);
     tc_fence_after();
   }
 
@@ -479,7 +487,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(TCOLS) : "memory");
+  if ((tid_all >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(TCOLS) : "memory");
 }
 
 
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(288, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
 }
 
 template <int STAGE, bool WG>
-__global__ void __launch_bounds__(128, 1) bwd_tc_kernel(BwdTcArgs a) {
+__global__ void __launch_bounds__(256, 1) bwd_tc_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
   const int role = blockIdx.y;
   if ((int)blockIdx.x >= a.ctas[role]) return;
@@ -1230,13 +1238,13 @@ int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage) {
 
 template <int STAGE, bool WG>
 static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStream_t s) {
-  const size_t smem = (size_t)((WG ? 16384 + 8192 : 4096) + MlpPackTCB::total()) * 4 + 1024;
+  const size_t smem = (size_t)((WG ? 16384 + 8192 : 8192) + MlpPackTCB::total()) * 4 + 1024;
   if (WG) {
     ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd_tc_wg_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
   } else {
     ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 128, smem, s>>>(a);
+    bwd_tc_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
   }
   ENS_CHECK_CUDA();
   return ENS_OK;
@@ -1288,7 +1296,8 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     if (!(r < ndec || (r == 3 && nroles == 4))) continue;
     int64_t n = (int64_t)(sms * cost[r] / tot);
     if (n < 1) n = 1;
-    if (n > a.n_tiles) n = a.n_tiles;
+    const int64_t cap = wg ? a.n_tiles : (a.n_tiles + 1) / 2;      // pose-only: two tiles in flight per CTA
+    if (n > cap) n = cap;
     a.ctas[r] = (int)n;
     if ((int)n > max_ctas) max_ctas = (int)n;
   }
