@@ -57,6 +57,7 @@ struct BwdTcArgs {
   float *raw_acc;           // [4 roles][RAW_FLOATS]
   float *gp;                // [3 planes][P][3], or null
   int ctas[4];              // persistent CTAs per role
+  float *gu_buf;            // split backward: g_u rows, [3 decoders][n_tiles][5 blocks][128][32], data kernel -> wgrad kernel
   long long *dbg;           // optional timestamps (tools/time_passes.py)
 };
 
@@ -94,7 +95,9 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32]) {
   return mine + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
-// stage one point's 32 values as row `pt` of an MN-major [128][32] block pair (value, TF32 remainder)
+// stage one point's 32 values as row `pt` of an MN-major [128][32] block pair (value, TF32 remainder).
+// (Lanes pt and pt + 4 of a quarter-warp store hit the same banks -- a 2-way conflict on every store.  Swapping the two
+// 16-byte halves for lanes with bit 2 of pt set removes it at the price of 8 selects per store pair; measured: no gain.)
 __device__ __forceinline__ void stage_row(float *__restrict__ hi, float *__restrict__ lo, int pt, const float (&v)[32]) {
   float *rh = hi + pt * 32, *rl = lo + pt * 32;
   const int sw = pt & 3;
@@ -122,7 +125,9 @@ __device__ __forceinline__ void issue_wgrad(uint32_t acc, uint32_t sA, uint32_t 
   for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
 }
 
-template <int ROLE, bool WG>
+// SPLIT (with !WG): the data-gradient half of the split mapping backward -- the pose-only chain, which additionally writes
+// every block's g_u row for wgrad (bwd_tc_wg_kernel<STAGE, true>) and keeps the sums that need no GEMM (bias sums, dB).
+template <int ROLE, bool WG, bool SPLIT = false>
 __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw) {
   constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
   constexpr int CD = (LEVEL == ENS_LEVEL_FINE) ? 64 : 32;
@@ -145,7 +150,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
   float *sw = sNB + (WG ? 8192 : 0);
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float4 sP[128];                           // p.float() of the tile's points (dB reduction, WG only)
+  __shared__ float4 sP[256];                           // p.float() of the tile's points (dB reduction), per tile group
   const int tid = tid_all & 127, warp = tid >> 5, lane = tid & 31;      // thread / warp WITHIN the tile group
   uint64_t *const barp = &bars[grp];
   float *stile = sMB + warp * 1024;
@@ -241,7 +246,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
       __syncwarp();
       stage_row(sMB + 4096, sMB + 3 * 4096, tid, c);
     }
-    if (WG && TAIL) sP[tid] = make_float4(p32[0], p32[1], p32[2], 0.f);
+    if ((WG || SPLIT) && TAIL) sP[128 * grp + tid] = make_float4(p32[0], p32[1], p32[2], 0.f);
 
     // ---- g_h4 = Wo^T g_out ----
     float g[32];
@@ -289,6 +294,15 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
         const uint32_t mw = valid ? a.save_m[(int64_t)DEC * a.m_stride + (pt >> 5) * 160 + i * 32 + (pt & 31)] : 0u;
 #pragma unroll
         for (int k = 0; k < 32; ++k) gu[k] = ((mw >> k) & 1u) ? g[k] : 0.f;
+      }
+      if (SPLIT) {
+        // the row the weight-gradient kernel multiplies with [r_{i-1} | c | e]: 128 B per thread, stays in L2
+        float4 *dst = reinterpret_cast<float4 *>(a.gu_buf + ((((int64_t)DEC * a.n_tiles + tile) * 5 + i) * 128 + tid) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(gu[4 * q], gu[4 * q + 1], gu[4 * q + 2], gu[4 * q + 3]);
+        const float bs = warp_colsum32(gu);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (k == i) bhat[k] += bs;
       }
       if (WG) {
         const float bs = warp_colsum32(gu);
@@ -407,7 +421,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
         }
         __syncwarp();
       }
-      if (WG || want_rays) {
+      if (WG || SPLIT || want_rays) {
         const float *B = sw + PB::off_B();
         float gpe[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -423,7 +437,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
             ge[k] = gq;
             gpe[0] = fmaf(bx, gq, gpe[0]); gpe[1] = fmaf(by, gq, gpe[1]); gpe[2] = fmaf(bz, gq, gpe[2]);
           }
-          if (WG) {
+          if (WG || SPLIT) {
             // dB[r][32 jc + k] = sum_pt p[pt][r] g_q[pt][k]: transpose through the warp's tile, lane k walks its column
             __syncwarp();
 #pragma unroll
@@ -434,7 +448,7 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
               const float v = stile[r * 32 + (lane ^ ((r & 3) << 3))];
-              const float4 pr = sP[32 * warp + r];
+              const float4 pr = sP[128 * grp + 32 * warp + r];
               s0 = fmaf(pr.x, v, s0); s1 = fmaf(pr.y, v, s1); s2 = fmaf(pr.z, v, s2);
             }
 #pragma unroll
@@ -478,6 +492,17 @@ __device__ __forceinline__ void bwd_tc_body(const BwdTcArgs &a, float *smem_raw)
       atomicAdd(raw + RAW_QO + o * 32 + lane, qo[o]);
       if (lane == 0) atomicAdd(raw + RAW_DBO + o, dbo[o]);
     }
+    if (TAIL) {
+#pragma unroll
+      for (int jc = 0; jc < 3; ++jc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) atomicAdd(raw + RAW_DB + r * 96 + 32 * jc + lane, dBacc[jc][r]);
+    }
+  }
+  if (SPLIT) {
+    float *raw = a.raw_acc + (int64_t)ROLE * RAW_FLOATS;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
     if (TAIL) {
 #pragma unroll
       for (int jc = 0; jc < 3; ++jc)
@@ -555,7 +580,10 @@ __device__ __forceinline__ void cta_sync288() { asm volatile("bar.sync 2, 288;" 
 __device__ __forceinline__ void cta_arrive_a() { asm volatile("bar.arrive 3, 160;" ::: "memory"); }
 __device__ __forceinline__ void cta_sync_a() { asm volatile("bar.sync 3, 160;" ::: "memory"); }
 
-template <int ROLE>
+// SPLIT: the weight-gradient half of the split mapping backward.  The same eight passes per tile, but the g_u rows come from
+// the data-gradient kernel (bwd_tc_kernel<STAGE, false, true>) through L2 instead of from this CTA's own chain: no data
+// GEMMs, no masks, no tails -- a pass is load + stage + 32 MMAs, with nothing serial between passes but the buffers.
+template <int ROLE, bool SPLIT = false>
 __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_raw) {
   constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
   constexpr int CD = (LEVEL == ENS_LEVEL_FINE) ? 64 : 32;
@@ -657,7 +685,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         const int i = pass_layer(ps);
         // the data-gradient GEMM goes out as soon as the E warps have put g_u_i into TMEM (barrier 3); they stage the same
         // rows for the weight-gradient pass while it runs
-        if (i >= 1) {
+        if (!SPLIT && i >= 1) {
           cta_sync_a();
           tc_fence_after();
           // [g_h | g_c | g_e] += g_u [WhT_i ; MT_{i-1} ; W3eT]
@@ -665,7 +693,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
           else if (i == 3) issue_gemm<32, 32, 160>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(3), PB::TOT(), 1u);
           else issue_gemm<32, 32, 64>(tb0 + TB_DH, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(i), PB::TOT(), 1u);
           umma_commit(&barD);
-        } else if (i == 0 && TAIL) {
+        } else if (!SPLIT && i == 0 && TAIL) {
           cta_sync_a();
           tc_fence_after();
           issue_gemm<32, 32, 96>(tb0 + TB_DE, tb0 + TB_XH, tb0 + TB_XL, swb, PB::off_G(0), PB::TOT(), 1u);
@@ -687,7 +715,10 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
       for (int i = 0; i < 5; ++i)
         mw[i] = valid ? __ldg(a.save_m + (int64_t)DEC * a.m_stride + (pt >> 5) * 160 + i * 32 + (pt & 31)) : 0u;
       float g[32];
-      {
+      const float *gubase = SPLIT ? a.gu_buf + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32 : nullptr;
+      if (SPLIT) {
+        load_row32(gubase + pass_layer(0) * 4096, g);             // pass 0's g_u row (the next one is fetched a pass ahead)
+      } else {
         const float *Wo = sw + PB::off_Wo();
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -702,7 +733,16 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
       for (int ps = 0; ps < NPASS; ++ps) {
         const int i = pass_layer(ps);
         ENS_DBG(ps, 0);
-        if (i >= 0) {
+        if (SPLIT && i >= 0) {
+          if (!first) { mbar_wait(&barW, pw); pw ^= 1; }
+          stage_row(sNB, sNB + 4096, pl, g);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          // the next block pass's row, in flight during this pass's MMAs and the Fourier passes in between
+          int nl = -1;
+#pragma unroll
+          for (int q = NPASS - 1; q >= 0; --q) if (q > ps && pass_layer(q) >= 0) nl = pass_layer(q);
+          if (nl >= 0) load_row32(gubase + nl * 4096, g);
+        } else if (i >= 0) {
           uint32_t m = 0u;
 #pragma unroll
           for (int k = 0; k < 5; ++k) if (k == i) m = mw[k];
@@ -740,13 +780,13 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         tc_fence_before();
         cta_sync288();
         ENS_DBG(ps, 4);
-        if (i >= 1) {
+        if (!SPLIT && i >= 1) {
           mbar_wait(&barD, pd); pd ^= 1;
           tc_fence_after();
           ENS_DBG(ps, 5);
           tmem_ld32(tb + TB_DH, g);
           tmem_zero32(tb + TB_DH);                    // the next block's GEMM accumulates into zero
-        } else if (i == 0 && TAIL) {
+        } else if (!SPLIT && i == 0 && TAIL) {
           mbar_wait(&barD, pd); pd ^= 1;              // g_e complete
           tc_fence_after();
         }
@@ -754,7 +794,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
       }
       ENS_DBG(8, 2);
       // ---- tail: feature gradient -> grid scatter + coordinate gradient; embedding gradient ----
-      if (TAIL) {
+      if (TAIL && !SPLIT) {
         mbar_wait(&barW, pw); pw ^= 1;                // last pass done: the N-side block doubles as this warp's 32x32 tile
         first = true;                                 // ... and that phase is consumed
         tc_fence_after();
@@ -888,7 +928,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
         ENS_DBG(ps, 4);
         ENS_DBG(ps, 5);
       }
-      if (TAIL) {
+      if (TAIL && !SPLIT) {
         // ---- Fourier backward (the E warps do the trilinear backward meanwhile): g_q = g_e cos(p B), d L / d p += B g_q, dB ----
         mbar_wait(&barW, pw); pw ^= 1;                // last pass done (so is every data-gradient GEMM issued before it):
         first = true;                                 // slot B doubles as this warp's 32x32 tile; that phase is consumed
@@ -955,10 +995,12 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
 #pragma unroll
       for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
+    if (!SPLIT) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
+      for (int i = 0; i < 5; ++i) atomicAdd(raw + RAW_BHAT + i * 32 + lane, bhat[i]);
+    }
   } else {
-    if (TAIL) {
+    if (TAIL && !SPLIT) {
 #pragma unroll
       for (int jc = 0; jc < 3; ++jc)
 #pragma unroll
@@ -976,25 +1018,25 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(512u) : "memory");
 }
 
-template <int STAGE>
+template <int STAGE, bool SPLIT = false>
 __global__ void __launch_bounds__(288, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
   const int role = blockIdx.y;
   if ((int)blockIdx.x >= a.ctas[role]) return;
-  if (role == ROLE_MIDDLE) bwd_tc_wg_body<ROLE_MIDDLE>(a, smem);
-  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE>(a, smem); }
-  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_wg_body<ROLE_COLOR>(a, smem); }
-  else { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE_CM>(a, smem); }
+  if (role == ROLE_MIDDLE) bwd_tc_wg_body<ROLE_MIDDLE, SPLIT>(a, smem);
+  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE, SPLIT>(a, smem); }
+  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_wg_body<ROLE_COLOR, SPLIT>(a, smem); }
+  else { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_wg_body<ROLE_FINE_CM, SPLIT>(a, smem); }
 }
 
-template <int STAGE, bool WG>
+template <int STAGE, bool WG, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 1) bwd_tc_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
   const int role = blockIdx.y;
   if ((int)blockIdx.x >= a.ctas[role]) return;
-  if (role == ROLE_MIDDLE) bwd_tc_body<ROLE_MIDDLE, WG>(a, smem);
-  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE, WG>(a, smem); }
-  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_body<ROLE_COLOR, WG>(a, smem); }
+  if (role == ROLE_MIDDLE) bwd_tc_body<ROLE_MIDDLE, WG, SPLIT>(a, smem);
+  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) bwd_tc_body<ROLE_FINE, WG, SPLIT>(a, smem); }
+  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) bwd_tc_body<ROLE_COLOR, WG, SPLIT>(a, smem); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1230,21 +1272,37 @@ __global__ void __launch_bounds__(NT_MMA) place_bwd_kernel(DevScene sc, RayArgs 
 }
 
 // workspace: points [P][3] f64 | z [P] f64 | g_out [P][4] | g_p planes [3][P][3] | raw sums [4][RAW_FLOATS]
-int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage) {
-  if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
-  const int64_t P = n_rays * (int64_t)S;
-  return P * (24 + 8 + 16 + 72) + 4 * (int64_t)RAW_FLOATS * 4 + 256;
+static bool use_split_tc() {
+  const char *v = std::getenv("ENS_BWD_TC_SPLIT");          // 1: data-gradient kernel + weight-gradient kernel (A/B; measured slower)
+  return v && v[0] == '1';
 }
 
-template <int STAGE, bool WG>
+// ... | with decoder gradients (split backward): the g_u rows, [3 decoders][n_tiles][5][128][32] f32
+int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage, bool wg) {
+  if (stage == ENS_STAGE_COARSE || n_rays <= 0 || S < 1) return 0;
+  const int64_t P = n_rays * (int64_t)S;
+  const int64_t n_tiles = (P + 127) / 128;
+  return P * (24 + 8 + 16 + 72) + 4 * (int64_t)RAW_FLOATS * 4 + 256 + 256 + ((wg && use_split_tc()) ? 3 * n_tiles * 5 * 4096 * 4 : 0);
+}
+
+
+// MODE 0: pose-only chain; 1: fused data + weight gradients; 2: split -- data-gradient kernel; 3: split -- weight-gradient kernel
+template <int STAGE, int MODE>
 static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStream_t s) {
-  const size_t smem = (size_t)((WG ? 16384 + 8192 : 8192) + MlpPackTCB::total()) * 4 + 1024;
-  if (WG) {
-    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_wg_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
+  constexpr bool WGK = MODE == 1 || MODE == 3;
+  const size_t smem = (size_t)((WGK ? 16384 + 8192 : 8192) + MlpPackTCB::total()) * 4 + 1024;
+  if (MODE == 1) {
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_tc_wg_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
+  } else if (MODE == 3) {
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_tc_wg_kernel<STAGE, true><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
+  } else if (MODE == 2) {
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_tc_kernel<STAGE, false, true><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
   } else {
-    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
+    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_tc_kernel<STAGE, false, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
   }
   ENS_CHECK_CUDA();
   return ENS_OK;
@@ -1255,7 +1313,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   const int64_t R = b.ra.R;
   const int S = b.ra.S;
   const int64_t P = R * (int64_t)S;
-  if (!workspace || workspace_bytes < tc_bwd_workspace_bytes(R, S, stage)) return ENS_ESHAPE;
+  if (!workspace || workspace_bytes < tc_bwd_workspace_bytes(R, S, stage, wg)) return ENS_ESHAPE;
   if (b.save_masks == nullptr || (wg && b.save_r == nullptr)) return ENS_EINVAL;
   char *base = reinterpret_cast<char *>(workspace);
   double *pts = reinterpret_cast<double *>(base);
@@ -1263,6 +1321,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   float4 *gout = reinterpret_cast<float4 *>(base + P * 32);
   float *gp = reinterpret_cast<float *>(base + P * 48);
   float *raw = reinterpret_cast<float *>(base + ((P * 120 + 255) / 256) * 256);
+  float *gu_buf = raw + 4 * RAW_FLOATS + 64;
   const bool want_rays = b.g_rays_o != nullptr || b.g_rays_d != nullptr;
 
   b.ra.rpc = NT_MMA / S;
@@ -1278,34 +1337,54 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   a.save_r = b.save_r; a.save_m = b.save_masks; a.m_stride = b.n_tiles * 160;
   for (int l = 0; l < 4; ++l) a.ggrid[l] = b.ggrid[l];
   a.raw_acc = raw; a.gp = want_rays ? gp : nullptr;
+  a.gu_buf = wg ? gu_buf : nullptr;
   {
     const char *v = std::getenv("ENS_BWD_TC_DBG");          // tools/time_passes.py: device address of a long long[640]
     a.dbg = v ? reinterpret_cast<long long *>(std::strtoull(v, nullptr, 0)) : nullptr;
   }
   const int sms = sm_count();
-  // persistent CTAs per role, in proportion to the work of a tile (the FINE_CM role runs the hidden chain only)
   const int ndec = stage == ENS_STAGE_MIDDLE ? 1 : (stage == ENS_STAGE_FINE ? 2 : 3);
-  const int nroles = (wg && ndec > 1) ? 4 : ndec;
+  const bool split = wg && use_split_tc();
+  // persistent CTAs per role, in proportion to the work of a tile (the FINE_CM role runs the hidden chain only)
   // (a greedy split that also evens out the round quantisation -- 42 / 47 / 44 / 15 CTAs for 375 tiles -- measured 4-5 %
   // SLOWER than this proportional one in the same session, at 1000 and at 16 384 rays)
-  const double cost[4] = {1.0, 1.0, 1.0, 0.36};
-  double tot = 0.0;
-  for (int r = 0; r < 4; ++r) { a.ctas[r] = 0; if (r < ndec || (r == 3 && nroles == 4)) tot += cost[r]; }
-  int max_ctas = 0;
-  for (int r = 0; r < 4; ++r) {
-    if (!(r < ndec || (r == 3 && nroles == 4))) continue;
-    int64_t n = (int64_t)(sms * cost[r] / tot);
-    if (n < 1) n = 1;
-    const int64_t cap = wg ? a.n_tiles : (a.n_tiles + 1) / 2;      // pose-only: two tiles in flight per CTA
-    if (n > cap) n = cap;
-    a.ctas[r] = (int)n;
-    if ((int)n > max_ctas) max_ctas = (int)n;
+  auto deal = [&](int nroles, bool two_tiles, int &max_ctas) {
+    const double cost[4] = {1.0, 1.0, 1.0, 0.36};
+    double tot = 0.0;
+    for (int r = 0; r < 4; ++r) { a.ctas[r] = 0; if (r < ndec || (r == 3 && nroles == 4)) tot += cost[r]; }
+    max_ctas = 0;
+    for (int r = 0; r < 4; ++r) {
+      if (!(r < ndec || (r == 3 && nroles == 4))) continue;
+      int64_t n = (int64_t)(sms * cost[r] / tot);
+      if (n < 1) n = 1;
+      const int64_t cap = two_tiles ? (a.n_tiles + 1) / 2 : a.n_tiles;      // two tiles in flight per CTA
+      if (n > cap) n = cap;
+      a.ctas[r] = (int)n;
+      if ((int)n > max_ctas) max_ctas = (int)n;
+    }
+  };
+  int rc = ENS_OK, max_ctas = 0;
+#define ENS_TCB(MODE, NR)                                                                 \
+  (stage == ENS_STAGE_MIDDLE ? launch_bwd_tc<ENS_STAGE_MIDDLE, MODE>(a, NR, max_ctas, s)  \
+   : stage == ENS_STAGE_FINE ? launch_bwd_tc<ENS_STAGE_FINE, MODE>(a, NR, max_ctas, s)    \
+                             : launch_bwd_tc<ENS_STAGE_COLOR, MODE>(a, NR, max_ctas, s))
+  if (!wg) {
+    deal(ndec, true, max_ctas);
+    rc = ENS_TCB(0, ndec);
+  } else if (split) {
+    // data gradients (two tile groups per CTA; writes the g_u rows, bias sums, dB, grid scatter, d L / d p) ...
+    deal(ndec, true, max_ctas);
+    rc = ENS_TCB(2, ndec);
+    if (rc != ENS_OK) return rc;
+    // ... then the weight-gradient GEMMs over the point dimension
+    const int nroles = ndec > 1 ? 4 : ndec;
+    deal(nroles, false, max_ctas);
+    rc = ENS_TCB(3, nroles);
+  } else {
+    const int nroles = ndec > 1 ? 4 : ndec;
+    deal(nroles, false, max_ctas);
+    rc = ENS_TCB(1, nroles);
   }
-  int rc;
-#define ENS_TCB(ST) (wg ? launch_bwd_tc<ST, true>(a, nroles, max_ctas, s) : launch_bwd_tc<ST, false>(a, nroles, max_ctas, s))
-  if (stage == ENS_STAGE_MIDDLE) rc = ENS_TCB(ENS_STAGE_MIDDLE);
-  else if (stage == ENS_STAGE_FINE) rc = ENS_TCB(ENS_STAGE_FINE);
-  else rc = ENS_TCB(ENS_STAGE_COLOR);
 #undef ENS_TCB
   if (rc != ENS_OK) return rc;
   if (wg) {
@@ -1317,7 +1396,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
     ENS_CHECK_CUDA();
   }
   if (want_rays) {
-    rays_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(gp, wg ? 2 * ndec : ndec, z, R, S, b.g_rays_o, b.g_rays_d);
+    rays_reduce_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(gp, (wg && !split) ? 2 * ndec : ndec, z, R, S, b.g_rays_o, b.g_rays_d);
     ENS_CHECK_CUDA();
   }
   return ENS_OK;

@@ -296,7 +296,7 @@ inline int64_t tc_saved3_bytes(int64_t n_rays, int S, int stage, int64_t *r_byte
 }
 // tcgen05 backward (ens_bwd_tc.cu)
 int tc_render_bwd(BwdArgs &a, int stage, bool wg, void *workspace, int64_t workspace_bytes, cudaStream_t s);
-int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage);
+int64_t tc_bwd_workspace_bytes(int64_t n_rays, int S, int stage, bool wg);
 int tc_render_fwd(FwdArgs &a, int stage, void *scratch, int64_t scratch_bytes, cudaStream_t s);
 int64_t tc_fwd_scratch_bytes(int64_t n_rays, int S, int stage);
 int64_t mma_fwd_saved_bytes(int64_t n_rays, int S, int stage, int want_h, int64_t *n_tiles, int64_t *h_offset);

@@ -1022,7 +1022,7 @@ static bool use_tc_backward() {
 
 extern "C" int64_t ens_bwd_workspace_bytes(int64_t n_rays, int n_samples_total, int want_decoder_grads) {
   if (n_rays <= 0 || n_samples_total <= 0) return 0;
-  const int64_t tc = tc_bwd_workspace_bytes(n_rays, n_samples_total, ENS_STAGE_COLOR);
+  const int64_t tc = tc_bwd_workspace_bytes(n_rays, n_samples_total, ENS_STAGE_COLOR, want_decoder_grads != 0);
   if (!want_decoder_grads) return tc;
   const int64_t fma = (n_rays * (int64_t)n_samples_total + 1) * 160 * (int64_t)sizeof(float);   // +1: dump row for idle lanes
   const int64_t mma = mma_bwd_workspace_bytes(n_rays, n_samples_total);
@@ -1101,7 +1101,7 @@ extern "C" int ens_render_bwd(const EnsScene *scene, const EnsRenderCfg *cfg, in
   if (wg && saved_covers && (!workspace || workspace_bytes < ens_bwd_workspace_bytes(n_rays, S, 1))) a.hscratch = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   if (saved_with_activations == 2 && !wg && use_tc_backward() && workspace != nullptr &&
-      workspace_bytes >= tc_bwd_workspace_bytes(n_rays, S, stage)) {
+      workspace_bytes >= tc_bwd_workspace_bytes(n_rays, S, stage, false)) {
     rc = tc_render_bwd(a, stage, false, workspace, workspace_bytes, s);
     if (rc != ENS_EUNSUPPORTED) return rc;
   }

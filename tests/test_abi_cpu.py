@@ -36,10 +36,11 @@ def test_sizes_match_reference_parameter_counts(built):
     assert L.ens_packed_decoder_floats(1) % 4 == 0 and L.ens_packed_decoder_floats(2) % 4 == 0
     # pose-only backward: optional scratch of the tcgen05 backward = per point g_raw/g_c rows (24 + 8 + 16 + 72 B) + four
     # raw weight-gradient accumulator sets of 17 152 floats + 256 B of counters
-    tc = 48000 * (24 + 8 + 16 + 72) + 4 * 17152 * 4 + 256
+    tc = 48000 * (24 + 8 + 16 + 72) + 4 * 17152 * 4 + 512
     assert L.ens_bwd_workspace_bytes(1000, 48, 0) == tc
     # 1000 rays x 48 samples = 1500 tiles of 32 points: split-backward scratch = g_h tiles (3 decoders x 5 x 4 KB per
     # tile) + mask words (3 x 5 x 128 B) + points (1 KB); it exceeds the recompute / FFMA activation scratch
+    # (ENS_BWD_TC_SPLIT=1 adds the g_u rows of the split tcgen05 backward: [3 decoders][375 tiles][5 blocks][128][32] f32)
     assert L.ens_bwd_workspace_bytes(1000, 48, 1) == max(tc, 1500 * (3 * 5 * 4096 + 3 * 5 * 128 + 1024))
     assert L.ens_bwd_workspace_bytes(1000, 48, 1) >= (48000 + 1) * 160 * 4
     # saved-for-backward buffer of the forward: masks only / masks + five activation tiles per decoder

@@ -859,3 +859,31 @@ def test_room0_gradients_meet_1e3_with_the_kernels_own_relu_decisions():
     print("relu decisions that differ from the oracle's:", flips, " worst max-norm / elementwise error:",
           max(v[0] for v in worst.values()), max(v[1] for v in worst.values()))
     assert not bad, bad
+
+
+def test_split_tcgen05_backward_is_an_equivalent_ab_path(tiny, monkeypatch):
+    """ENS_BWD_TC_SPLIT=1: data-gradient kernel (two tile groups, writes the g_u rows) + weight-gradient kernel, instead of the
+    fused kernel.  Same raw sums -> same unfolded gradients (atomic order aside)."""
+    scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
+    g = tiny["g"]
+    ro = torch.from_numpy(g["color.d.rays_o"]).to(DEV); rd = torch.from_numpy(g["color.d.rays_d"]).to(DEV)
+    sd = torch.from_numpy(g["color.d.sample_depth"]).to(DEV)
+
+    def run():
+        for p in decoders.parameters():
+            p.grad = None
+        cg = {k: v.detach().clone().requires_grad_(True) for k, v in c.items()}
+        ro_ = ro.clone().requires_grad_(True); rd_ = rd.clone().requires_grad_(True)
+        d, u, col = renderer.render_batch_ray(cg, decoders, rd_, ro_, DEV, "color", gt_depth=sd)
+        (d.sum() + u.sum() + col.sum()).backward()
+        out = {"ro": ro_.grad.clone(), "rd": rd_.grad.clone()}
+        out.update({k: v.grad.clone() for k, v in cg.items() if v.grad is not None})
+        out.update({n: p.grad.clone() for n, p in decoders.named_parameters() if p.grad is not None})
+        return out
+    fused = run()
+    monkeypatch.setenv("ENS_BWD_TC_SPLIT", "1")
+    split = run()
+    assert set(fused) == set(split)
+    for k in fused:
+        assert rel_err(split[k].cpu().numpy(), fused[k].cpu().numpy()) < 1e-4, k
+
