@@ -554,6 +554,17 @@ __device__ __forceinline__ void issue_wgrad_loop(uint32_t acc, uint32_t sA, uint
   for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
 }
 
+// the same pass spread over TWO accumulators (even / odd k-steps): consecutive MMAs into one accumulator form a dependent
+// chain, and the wgrad kernel of the split backward has the TMEM columns to break it (the halves are added at the flush)
+__device__ __forceinline__ void issue_wgrad_loop2(uint32_t acc0, uint32_t acc1, uint32_t sA, uint32_t sB) {
+  constexpr uint32_t IDESC = tc_idesc_mn(128, 32);
+  const uint64_t da = umma_desc_mn(sA, 16384u), dbh = umma_desc_mn(sB, 16384u), dbl = umma_desc_mn(sB + 16384u, 16384u);
+#pragma unroll 4
+  for (int ks = 0; ks < 16; ++ks) umma_ss((ks & 1) ? acc1 : acc0, da + (uint64_t)(64 * ks), dbl + (uint64_t)(64 * ks), IDESC, 1u);
+#pragma unroll 4
+  for (int ks = 0; ks < 16; ++ks) umma_ss((ks & 1) ? acc1 : acc0, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
+}
+
 // the k-step `ks` (8 of the K columns) of  D += A[128 x K] * W[N x K]^T  in 3xTF32 -- see issue_gemm
 template <int KMAT, int N>
 __device__ __forceinline__ void issue_gemm_k(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t sw_base, int w_off, int tot, int ks) {
@@ -580,9 +591,9 @@ __device__ __forceinline__ void cta_sync288() { asm volatile("bar.sync 2, 288;" 
 __device__ __forceinline__ void cta_arrive_a() { asm volatile("bar.arrive 3, 160;" ::: "memory"); }
 __device__ __forceinline__ void cta_sync_a() { asm volatile("bar.sync 3, 160;" ::: "memory"); }
 
-// SPLIT: the weight-gradient half of the split mapping backward.  The same eight passes per tile, but the g_u rows come from
-// the data-gradient kernel (bwd_tc_kernel<STAGE, false, true>) through L2 instead of from this CTA's own chain: no data
-// GEMMs, no masks, no tails -- a pass is load + stage + 32 MMAs, with nothing serial between passes but the buffers.
+// SPLIT = true is the first form of the split backward's weight-gradient kernel (this kernel without data GEMMs, masks and
+// tails, single-buffered staging; 0.287 ms).  It is no longer launched -- wgrad_tc_kernel below, with two staging stages,
+// replaced it -- and is kept only as the record of that measurement.
 template <int ROLE, bool SPLIT = false>
 __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_raw) {
   constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
@@ -1018,6 +1029,268 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(512u) : "memory");
 }
 
+// =============================================================================================================
+// Weight-gradient kernel of the SPLIT backward (ENS_BWD_TC_SPLIT=1): the eight passes of bwd_tc_wg_kernel with the g_u rows read
+// from the data-gradient kernel's buffer -- no data GEMMs, so no weights in shared memory, and the room goes into a SECOND
+// staging stage: while the 32 MMAs of pass p read stage p % 2, the producers stage pass p + 1 into the other one.
+//   E warps (0..3): the N side (g_u row of the pass's block, value + remainder; the next row is prefetched) and the Fourier chunk
+//                   of the e-passes;  H warps (4..7): the M side (r rows, features, Fourier chunks) and the output-layer sums;
+//   warp 8 issues.  barW[s] (tcgen05.commit) says stage s has been read; a producer waits on it before it writes the stage again.
+// Slot B of BOTH stages holds the features (staged in passes 0 and 1); the e-passes that overwrite it (2 and 7) are followed by
+// a restore (pass 4) or by the next tile's passes 0 / 1.
+template <int ROLE>
+__device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_raw) {
+  constexpr int LEVEL = (ROLE == ROLE_MIDDLE) ? ENS_LEVEL_MIDDLE : (ROLE == ROLE_COLOR ? ENS_LEVEL_COLOR : ENS_LEVEL_FINE);
+  constexpr int CD = (LEVEL == ENS_LEVEL_FINE) ? 64 : 32;
+  constexpr int NO = (ROLE == ROLE_COLOR) ? 3 : 1;
+  constexpr int DEC = (ROLE == ROLE_MIDDLE) ? 0 : (ROLE == ROLE_COLOR ? 2 : 1);
+  constexpr bool TAIL = ROLE != ROLE_FINE_CM;
+  constexpr int CLEVEL = (ROLE == ROLE_FINE_CM) ? ENS_LEVEL_MIDDLE : LEVEL;
+  constexpr int NPASS = TAIL ? 8 : 5;
+  using PB = MlpPackTCB;
+
+  float *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) / 4;
+  // stage s: M side [hiA | hiB | loA | loB] (4 x 4096 floats), N side [g_hi | g_lo] (2 x 4096)
+  float *sB = base + 2 * 24576;      // Fourier matrix [3][EMBP]
+  __shared__ __align__(8) uint64_t barW[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool isE = warp < 4, isI = warp == 8;
+  const int pl = tid & 127, w4 = warp & 3;
+
+  {
+    const float *gB = a.sc.w[LEVEL] + off_tcb<CD>() + PB::off_B();
+    for (int i = tid; i < 3 * EMBP; i += 288) sB[i] = gB[i];
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&barW[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&barW[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb0 = tmem_base_s;
+  const uint32_t tb = tb0 + ((uint32_t)(32 * w4) << 16);
+  if (isE) {
+#pragma unroll 1
+    for (int c = 0; c < 32 * NPASS; c += 32) { tmem_zero32(tb + c); tmem_zero32(tb + 256 + c); }
+    tmem_st_done();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  uint32_t pwv[2] = {0u, 0u};        // phase parities of barW[s] as this thread has consumed them
+  bool pend[2] = {false, false};     // a pass that read stage s has been issued and this thread has not waited for it yet
+  int pcount = 0;                    // passes so far (stage = pcount & 1)
+  float dwor[NO], qo[NO], dbo[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) dwor[o] = qo[o] = dbo[o] = 0.f;
+  const int nctas = a.ctas[ROLE];
+  // block whose g_u row is the N side of a pass; e-passes (2, 3, 7) reuse the row of the block pass before them
+  auto pass_block = [](int p) { return TAIL ? (p == 0 ? 4 : (p <= 3 ? 3 : (p == 4 ? 2 : (p == 5 ? 1 : 0)))) : 4 - p; };
+  auto is_epass = [](int p) { return TAIL && (p == 2 || p == 3 || p == 7); };
+  auto wait_stage = [&](int st) {
+    if (pend[st]) { mbar_wait(&barW[st], pwv[st]); pwv[st] ^= 1u; pend[st] = false; }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+    const int64_t pt = tile * 128 + pl;
+    const bool valid = pt < a.P;
+    if (isI) {
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int st = pcount & 1;
+        tc_fence_before();
+        cta_sync288();
+        tc_fence_after();
+        issue_wgrad_loop2(tb0 + 32 * ps, tb0 + 256 + 32 * ps, smem_u32(base + st * 24576), smem_u32(base + st * 24576 + 16384));
+        umma_commit(&barW[st]);
+        __syncwarp();
+        ++pcount;
+      }
+      continue;
+    }
+    double p[3] = {0.0, 0.0, 0.0};
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const double *pp = a.pts + pt * 3;
+      p[0] = pp[0]; p[1] = pp[1]; p[2] = pp[2];
+      g4 = a.gout[pt];
+    }
+    float pn[3], p32[3];
+    normalize64(p, a.sc.lo, a.sc.hi, pn);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p32[k] = __double2float_rn(p[k]);
+    float go[NO];
+    if (ROLE == ROLE_COLOR) { go[0] = g4.x; if (NO > 1) { go[1 % NO] = g4.y; go[2 % NO] = g4.z; } }
+    else go[0] = g4.w;
+
+    if (isE) {
+      // ================================ E warps: N side + one Fourier chunk per e-pass ================================
+      const float *gubase = a.gu_buf + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
+      float g[32], gn[32];
+      load_row32(gubase + pass_block(0) * 4096, g);
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int st = pcount & 1;
+        float *sM = base + st * 24576, *sN = sM + 16384;
+        if (ps > 0 && pass_block(ps) != pass_block(ps - 1)) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) g[k] = gn[k];
+        }
+        float ve[32];
+        if (is_epass(ps)) {
+          const int je = (ps == 2) ? 1 : 2;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            ve[k] = fast_sin(fmaf(p32[2], sB[2 * EMBP + 32 * je + k], fmaf(p32[1], sB[EMBP + 32 * je + k], p32[0] * sB[32 * je + k])));
+        }
+        wait_stage(st);
+        stage_row(sN, sN + 4096, pl, g);
+        if (is_epass(ps)) {
+          if (ps == 3) stage_row(sM, sM + 2 * 4096, pl, ve);                 // e2 -> slot A
+          else stage_row(sM + 4096, sM + 3 * 4096, pl, ve);                  // e1 / e2 -> slot B
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // the next block's row, in flight during the barrier and the passes that reuse this one
+        if (ps + 1 < NPASS && pass_block(ps + 1) != pass_block(ps)) load_row32(gubase + pass_block(ps + 1) * 4096, gn);
+        pend[st] = true;
+        tc_fence_before();
+        cta_sync288();
+        ++pcount;
+      }
+    } else {
+      // ================================ H warps: M side + output-layer sums ================================
+      const float *rbase = a.save_r + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
+      float c[32], rn[32];
+      if (TAIL) load_row32(rbase + 4 * 4096, rn);                 // r_4: in flight during the gather
+      const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
+      const int st0 = pcount & 1;
+      float *sM0 = base + st0 * 24576;
+      wait_stage(st0);                                            // pass 0's stage: its slot B takes the gather directly
+      float *tileB = sM0 + 4096 + w4 * 1024;
+      __syncwarp();
+      gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
+      if (TAIL) {
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          float t[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = go[o] * rn[k];
+          dwor[o] += warp_colsum32(t);
+          float sg = go[o];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, off);
+          dbo[o] += sg;
+        }
+        load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0
+      }
+      {
+        float *lrow = sM0 + 3 * 4096 + w4 * 1024 + lane * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int off = (4 * q) ^ ((lane & 3) << 3);
+          const float4 x = *reinterpret_cast<const float4 *>(tileB + lane * 32 + off);
+          c[4 * q] = x.x; c[4 * q + 1] = x.y; c[4 * q + 2] = x.z; c[4 * q + 3] = x.w;
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          *reinterpret_cast<float4 *>(lrow + off) = l;
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          float t[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = go[o] * c[k];
+          qo[o] += warp_colsum32(t);
+        }
+      }
+#pragma unroll 1
+      for (int ps = 0; ps < NPASS; ++ps) {
+        const int st = pcount & 1;
+        float *sM = base + st * 24576;
+        const int i = TAIL ? (ps == 0 ? 4 : (ps == 1 ? 3 : (ps == 4 ? 2 : (ps == 5 ? 1 : (ps == 6 ? 0 : -1))))) : 4 - ps;
+        float va[32];
+        if (TAIL) {
+          //   pass:    0   1   2      3      4   5   6    7
+          //   slot A:  r3  r2  e0     e2*    r1  r0  e0   e1        (* = staged by the E warps)
+          //   slot B:  c   c   e1*    .      c   .   .    e2*       (c: both stages hold the features)
+          const int ja = (ps == 2 || ps == 6) ? 0 : (ps == 7 ? 1 : -1);
+          if (ja >= 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              va[k] = fast_sin(fmaf(p32[2], sB[2 * EMBP + 32 * ja + k], fmaf(p32[1], sB[EMBP + 32 * ja + k], p32[0] * sB[32 * ja + k])));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) va[k] = rn[k];
+          }
+          // the next block pass's slot A (r_{i-2}) is fetched while this pass is staged
+          int nxt = -1;
+          if (ps + 1 < NPASS) nxt = (ps + 1 == 1) ? 3 : (ps + 1 == 4 ? 2 : (ps + 1 == 5 ? 1 : -1));
+          if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
+        }
+        wait_stage(st);
+        if (TAIL && ps != 3) stage_row(sM, sM + 2 * 4096, pl, va);
+        if (ps == 1 || (TAIL && ps == 4)) stage_row(sM + 4096, sM + 3 * 4096, pl, c);
+        (void)i;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        pend[st] = true;
+        tc_fence_before();
+        cta_sync288();
+        ++pcount;
+      }
+    }
+  }
+
+  // ---- flush the CTA's sums ----
+  if (!isI) { wait_stage(0); wait_stage(1); }
+  tc_fence_after();
+  float *raw = a.raw_acc + (int64_t)ROLE * RAW_FLOATS;
+  if (isI) {
+  } else if (isE) {
+#pragma unroll 1
+    for (int acc = 0; acc < NPASS; ++acc) {
+      float v[32], v2[32];
+      tmem_ld32(tb + 32 * acc, v);
+      tmem_ld32(tb + 256 + 32 * acc, v2);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] += v2[k];
+      float *dst = raw + acc * 2048 + (pl & 63) * 32;               // lanes 64..127 hold the remainder products of rows 0..63
+#pragma unroll
+      for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+      atomicAdd(raw + RAW_DWOR + o * 32 + lane, dwor[o]);
+      atomicAdd(raw + RAW_QO + o * 32 + lane, qo[o]);
+      if (lane == 0) atomicAdd(raw + RAW_DBO + o, dbo[o]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(512u) : "memory");
+}
+
+template <int STAGE>
+__global__ void __launch_bounds__(288, 1) wgrad_tc_kernel(BwdTcArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  const int role = blockIdx.y;
+  if ((int)blockIdx.x >= a.ctas[role]) return;
+  if (role == ROLE_MIDDLE) wgrad_tc_body<ROLE_MIDDLE>(a, smem);
+  else if (role == ROLE_FINE) { if constexpr (STAGE >= ENS_STAGE_FINE) wgrad_tc_body<ROLE_FINE>(a, smem); }
+  else if (role == ROLE_COLOR) { if constexpr (STAGE == ENS_STAGE_COLOR) wgrad_tc_body<ROLE_COLOR>(a, smem); }
+  else { if constexpr (STAGE >= ENS_STAGE_FINE) wgrad_tc_body<ROLE_FINE_CM>(a, smem); }
+}
+
 template <int STAGE, bool SPLIT = false>
 __global__ void __launch_bounds__(288, 1) bwd_tc_wg_kernel(BwdTcArgs a) {
   extern __shared__ __align__(128) float smem[];
@@ -1295,8 +1568,9 @@ static int launch_bwd_tc(const BwdTcArgs &a, int nroles, int max_ctas, cudaStrea
     ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd_tc_wg_kernel<STAGE, false><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
   } else if (MODE == 3) {
-    ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_wg_kernel<STAGE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_wg_kernel<STAGE, true><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem, s>>>(a);
+    const size_t smem3 = (size_t)(2 * 24576 + 3 * EMBP) * 4 + 1024;          // two staging stages + the Fourier matrix
+    ENS_CUDA_CALL(cudaFuncSetAttribute(wgrad_tc_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    wgrad_tc_kernel<STAGE><<<dim3((unsigned)max_ctas, (unsigned)nroles), 288, smem3, s>>>(a);
   } else if (MODE == 2) {
     ENS_CUDA_CALL(cudaFuncSetAttribute(bwd_tc_kernel<STAGE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd_tc_kernel<STAGE, false, true><<<dim3((unsigned)max_ctas, (unsigned)nroles), 256, smem, s>>>(a);
