@@ -1100,6 +1100,10 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
   };
 
   for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += nctas) {
+    const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && tile == (int64_t)nctas && (tid == 0 || tid == 128 || tid == 256);
+#define ENS_DBG(ps, slot) do { if (dbg_on) a.dbg[((ROLE * 10 + (ps)) * 2 + ((tid >> 7) & 1)) * 8 + (slot)] = clock64(); } while (0)
+#define ENS_DBGI(who, slot) do { if (dbg_on) a.dbg[((ROLE * 10 + 9) * 2 + (who)) * 8 + (slot)] = clock64(); } while (0)
+    ENS_DBG(8, 0);
     const int64_t pt = tile * 128 + pl;
     const bool valid = pt < a.P;
     if (isI) {
@@ -1109,9 +1113,11 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         tc_fence_before();
         cta_sync288();
         tc_fence_after();
+        ENS_DBGI(0, ps);
         issue_wgrad_loop2(tb0 + 32 * ps, tb0 + 256 + 32 * ps, smem_u32(base + st * 24576), smem_u32(base + st * 24576 + 16384));
         umma_commit(&barW[st]);
         __syncwarp();
+        ENS_DBGI(1, ps);
         ++pcount;
       }
       continue;
@@ -1144,6 +1150,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
 #pragma unroll
           for (int k = 0; k < 32; ++k) g[k] = gn[k];
         }
+        ENS_DBG(ps, 0);
         float ve[32];
         if (is_epass(ps)) {
           const int je = (ps == 2) ? 1 : 2;
@@ -1151,7 +1158,9 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
           for (int k = 0; k < 32; ++k)
             ve[k] = fast_sin(fmaf(p32[2], sB[2 * EMBP + 32 * je + k], fmaf(p32[1], sB[EMBP + 32 * je + k], p32[0] * sB[32 * je + k])));
         }
+        ENS_DBG(ps, 1);
         wait_stage(st);
+        ENS_DBG(ps, 2);
         stage_row(sN, sN + 4096, pl, g);
         if (is_epass(ps)) {
           if (ps == 3) stage_row(sM, sM + 2 * 4096, pl, ve);                 // e2 -> slot A
@@ -1161,8 +1170,10 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         // the next block's row, in flight during the barrier and the passes that reuse this one
         if (ps + 1 < NPASS && pass_block(ps + 1) != pass_block(ps)) load_row32(gubase + pass_block(ps + 1) * 4096, gn);
         pend[st] = true;
+        ENS_DBG(ps, 3);
         tc_fence_before();
         cta_sync288();
+        ENS_DBG(ps, 4);
         ++pcount;
       }
     } else {
@@ -1218,6 +1229,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         const int st = pcount & 1;
         float *sM = base + st * 24576;
         const int i = TAIL ? (ps == 0 ? 4 : (ps == 1 ? 3 : (ps == 4 ? 2 : (ps == 5 ? 1 : (ps == 6 ? 0 : -1))))) : 4 - ps;
+        ENS_DBG(ps, 0);
         float va[32];
         if (TAIL) {
           //   pass:    0   1   2      3      4   5   6    7
@@ -1237,17 +1249,23 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
           if (ps + 1 < NPASS) nxt = (ps + 1 == 1) ? 3 : (ps + 1 == 4 ? 2 : (ps + 1 == 5 ? 1 : -1));
           if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
         }
+        ENS_DBG(ps, 1);
         wait_stage(st);
+        ENS_DBG(ps, 2);
         if (TAIL && ps != 3) stage_row(sM, sM + 2 * 4096, pl, va);
         if (ps == 1 || (TAIL && ps == 4)) stage_row(sM + 4096, sM + 3 * 4096, pl, c);
         (void)i;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         pend[st] = true;
+        ENS_DBG(ps, 3);
         tc_fence_before();
         cta_sync288();
+        ENS_DBG(ps, 4);
         ++pcount;
       }
     }
+#undef ENS_DBG
+#undef ENS_DBGI
   }
 
   // ---- flush the CTA's sums ----
