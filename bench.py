@@ -1081,7 +1081,8 @@ def measure_other_configs(dev, renderer, decoders, c, frames, scene):
         p.requires_grad_(r)
     # the side measurements must never cost the headline line: a failure is reported in place of the entry
     for name, fn in (("mapping_variants", lambda: measure_mapping_variants(dev, renderer, decoders, c, frames, scene)),
-                     ("grid_adam", lambda: measure_grid_adam(dev)), ("event_loss", lambda: measure_event_loss(dev))):
+                     ("grid_adam", lambda: measure_grid_adam(dev)), ("event_loss", lambda: measure_event_loss(dev)),
+                     ("mapper_ops", lambda: measure_mapper_ops(dev))):
         try:
             out.update(fn())
         except Exception as e:      # pragma: no cover
@@ -1130,6 +1131,44 @@ def measure_event_loss(dev):
         return float(np.median(ts))
     return {"event_loss_102x180": {"ms": timed(fused), "torchvision_reference_lines_ms": timed(ref),
                                    "note": "eager, loss + backward to the predicted event image"}}
+
+
+def measure_mapper_ops(dev):
+    """SURVEY.md 8(f) rank 3 and the rest of rank 2: frustum feature selection (Mapper.py:115-186) on room0's fine grid,
+    keyframe overlap (Mapper.py:222-241) for 30 keyframes x 1600 points, UNet input assembly (event_net.py:74-87) at
+    102 x 180 -- wall clock per call including the host side (4x4 inverse, one pose copy), eager."""
+    import torch
+    import frustum_cases as fc
+    from evennicer_slam_b200.event_net import assemble_input
+    from evennicer_slam_b200.mapper_ops import FrustumSelector
+
+    def wall(fn, reps=20):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+    case = fc.mask_cases()["room0"]
+    sel = FrustumSelector(*case["cam"], case["bound"], dev)
+    depth = torch.from_numpy(case["depth"]).to(dev)
+    c2w = torch.from_numpy(case["c2w"]).to(dev)
+    shape = case["shapes"]["grid_fine"]
+    out = {"frustum_mask_room0_fine": {"voxels": int(np.prod(shape)), "ms": wall(lambda: sel.voxel_mask(c2w, "grid_fine", shape, depth)),
+                                       "note": "device bool [Z,Y,X] mask; the reference's numpy + cv2.remap code takes 22 ms for the same grid (oracle timing, tools/time_frustum.py)"}}
+    oc = fc.overlap_cases()["rpg"]
+    sel2 = FrustumSelector(*oc["cam"], fc.RPG_BOUND, dev)
+    kf = [torch.from_numpy(c).to(dev) for c in oc["kf_c2w"]]
+    pts = torch.rand(1600, 3, device=dev) * 4 - 2
+    out["keyframe_overlap_30x1600"] = {"ms": wall(lambda: sel2.keyframe_overlap_counts(pts, kf))}
+    a = torch.rand(102, 180, 3, device=dev, dtype=torch.float64)
+    b = torch.rand(102, 180, 3, device=dev, requires_grad=True)
+
+    def unet_in():
+        b.grad = None
+        assemble_input(a, b, 1.0).sum().backward()
+    out["unet_input_102x180"] = {"ms": wall(unet_in), "note": "assemble + backward into the rendered image, eager"}
+    return out
 
 
 def measure_grid_adam(dev):

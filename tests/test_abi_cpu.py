@@ -146,3 +146,14 @@ def test_decoder_tensors_cache_follows_the_live_parameters():
     assert _bound_floats(b) == (-1.0, 2.0, -3.0, 4.0, -5.0, 6.5)
     b[2, 1] = 7.0                                            # in-place edit bumps the version
     assert _bound_floats(b)[-1] == 7.0
+
+
+def test_round2_dropins_have_no_cpu_fallback():
+    """mapper_ops / event_net must refuse CPU tensors loudly instead of computing something else."""
+    import torch
+    from evennicer_slam_b200 import event_net, mapper_ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mapper_ops.FrustumSelector(8, 8, 5.0, 5.0, 3.5, 3.5, [[-1, 1], [-1, 1], [-1, 1]], "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        event_net.assemble_input(torch.zeros(4, 4, 3), torch.zeros(4, 4, 3))
+

@@ -887,3 +887,25 @@ def test_split_tcgen05_backward_is_an_equivalent_ab_path(tiny, monkeypatch):
     for k in fused:
         assert rel_err(split[k].cpu().numpy(), fused[k].cpu().numpy()) < 1e-4, k
 
+
+@pytest.mark.parametrize("var", ["ENS_TC_PIPE", "ENS_TC_MULTI"])
+def test_decode_ab_switches_are_bitwise_equivalent(tiny, monkeypatch, var):
+    """The pipelined gather (ENS_TC_PIPE) and the one-launch-per-stage forward (ENS_TC_MULTI) only change WHEN work is done:
+    outputs of eval_points and of a colour-stage render must be bit-identical with the switch off."""
+    scene, renderer, decoders, c = tiny["scene"], tiny["renderer"], tiny["decoders"], tiny["c"]
+    g = tiny["g"]
+    pts = torch.from_numpy(cases.eval_points_lattice(scene)).to(DEV)
+    ro = torch.from_numpy(g["color.d.rays_o"]).to(DEV); rd = torch.from_numpy(g["color.d.rays_d"]).to(DEV)
+    sd = torch.from_numpy(g["color.d.sample_depth"]).to(DEV)
+
+    def run():
+        with torch.no_grad():
+            ev = renderer.eval_points(pts, decoders, c, "color", DEV).clone()
+            d, u, col = renderer.render_batch_ray(c, decoders, rd, ro, DEV, "color", gt_depth=sd)
+        return ev, d.clone(), u.clone(), col.clone()
+    on = run()
+    monkeypatch.setenv(var, "0")
+    off = run()
+    for a, b in zip(on, off):
+        assert torch.equal(a, b)
+
