@@ -57,6 +57,8 @@ struct BwdTcArgs {
   float *raw_acc;           // [4 roles][RAW_FLOATS]
   float *gp;                // [3 planes][P][3], or null
   int ctas[4];              // persistent CTAs per role
+  int exp_flags;            // ENS_WGRAD_EXP (timing experiments on wgrad_tc_kernel only; results are invalid when set):
+                            // 1 = producers stage the first tile only, 2 = issue the g_hi MMAs only, 4 = no MMAs at all
   float *gu_buf;            // split backward: g_u rows, [3 decoders][n_tiles][5 blocks][128][32], data kernel -> wgrad kernel
   long long *dbg;           // optional timestamps (tools/time_passes.py)
 };
@@ -554,6 +556,13 @@ __device__ __forceinline__ void issue_wgrad_loop(uint32_t acc, uint32_t sA, uint
   for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
 }
 
+// (timing experiment) only the value half of the N side
+__device__ __forceinline__ void issue_wgrad_half(uint32_t acc, uint32_t sA, uint32_t sB) {
+  constexpr uint32_t IDESC = tc_idesc_mn(128, 32);
+  const uint64_t da = umma_desc_mn(sA, 16384u), dbh = umma_desc_mn(sB, 16384u);
+#pragma unroll 4
+  for (int ks = 0; ks < 16; ++ks) umma_ss(acc, da + (uint64_t)(64 * ks), dbh + (uint64_t)(64 * ks), IDESC, 1u);
+}
 // the same pass spread over TWO accumulators (even / odd k-steps): consecutive MMAs into one accumulator form a dependent
 // chain, and the wgrad kernel of the split backward has the TMEM columns to break it (the halves are added at the flush)
 __device__ __forceinline__ void issue_wgrad_loop2(uint32_t acc0, uint32_t acc1, uint32_t sA, uint32_t sB) {
@@ -1114,7 +1123,9 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         cta_sync288();
         tc_fence_after();
         ENS_DBGI(0, ps);
-        issue_wgrad_loop2(tb0 + 32 * ps, tb0 + 256 + 32 * ps, smem_u32(base + st * 24576), smem_u32(base + st * 24576 + 16384));
+        if (a.exp_flags & 4) { }
+        else if (a.exp_flags & 2) issue_wgrad_half(tb0 + 32 * ps, smem_u32(base + st * 24576), smem_u32(base + st * 24576 + 16384));
+        else issue_wgrad_loop2(tb0 + 32 * ps, tb0 + 256 + 32 * ps, smem_u32(base + st * 24576), smem_u32(base + st * 24576 + 16384));
         umma_commit(&barW[st]);
         __syncwarp();
         ENS_DBGI(1, ps);
@@ -1161,8 +1172,9 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         ENS_DBG(ps, 1);
         wait_stage(st);
         ENS_DBG(ps, 2);
-        stage_row(sN, sN + 4096, pl, g);
-        if (is_epass(ps)) {
+        const bool do_stage = !(a.exp_flags & 1) || tile == (int64_t)blockIdx.x;
+        if (do_stage) stage_row(sN, sN + 4096, pl, g);
+        if (is_epass(ps) && do_stage) {
           if (ps == 3) stage_row(sM, sM + 2 * 4096, pl, ve);                 // e2 -> slot A
           else stage_row(sM + 4096, sM + 3 * 4096, pl, ve);                  // e1 / e2 -> slot B
         }
@@ -1252,8 +1264,9 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         ENS_DBG(ps, 1);
         wait_stage(st);
         ENS_DBG(ps, 2);
-        if (TAIL && ps != 3) stage_row(sM, sM + 2 * 4096, pl, va);
-        if (ps == 1 || (TAIL && ps == 4)) stage_row(sM + 4096, sM + 3 * 4096, pl, c);
+        const bool do_stage = !(a.exp_flags & 1) || tile == (int64_t)blockIdx.x;
+        if (do_stage && TAIL && ps != 3) stage_row(sM, sM + 2 * 4096, pl, va);
+        if (do_stage && (ps == 1 || (TAIL && ps == 4))) stage_row(sM + 4096, sM + 3 * 4096, pl, c);
         (void)i;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         pend[st] = true;
@@ -1674,6 +1687,7 @@ int tc_render_bwd(BwdArgs &b, int stage, bool wg, void *workspace, int64_t works
   for (int l = 0; l < 4; ++l) a.ggrid[l] = b.ggrid[l];
   a.raw_acc = raw; a.gp = want_rays ? gp : nullptr;
   a.gu_buf = wg ? gu_buf : nullptr;
+  { const char *v = std::getenv("ENS_WGRAD_EXP"); a.exp_flags = v ? std::atoi(v) : 0; }
   {
     const char *v = std::getenv("ENS_BWD_TC_DBG");          // tools/time_passes.py: device address of a long long[640]
     a.dbg = v ? reinterpret_cast<long long *>(std::strtoull(v, nullptr, 0)) : nullptr;
