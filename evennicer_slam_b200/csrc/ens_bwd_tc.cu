@@ -58,7 +58,8 @@ struct BwdTcArgs {
   float *gp;                // [3 planes][P][3], or null
   int ctas[4];              // persistent CTAs per role
   int exp_flags;            // ENS_WGRAD_EXP (timing experiments on wgrad_tc_kernel only; results are invalid when set):
-                            // 1 = producers stage the first tile only, 2 = issue the g_hi MMAs only, 4 = no MMAs at all
+                            // 1 = producers stage the first tile only, 2 = issue the g_hi MMAs only, 4 = no MMAs at all,
+                            // 8 = no sin, 16 = no row loads, 32 = no feature gather / output-layer sums
   float *gu_buf;            // split backward: g_u rows, [3 decoders][n_tiles][5 blocks][128][32], data kernel -> wgrad kernel
   long long *dbg;           // optional timestamps (tools/time_passes.py)
 };
@@ -863,6 +864,7 @@ __device__ __forceinline__ void bwd_tc_wg_body(const BwdTcArgs &a, float *smem_r
       // ================================ H warps ================================
       float c[32], rn[32];
       if (TAIL) load_row32(rbase + 4 * 4096, rn);                 // r_4: in flight during the gather
+      // (an L2 prefetch of the next tile's saved rows from here, a whole tile ahead, was measured: no gain at 1000 rays, -2 % at 16 k)
       const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
       if (!first) { mbar_wait(&barW, pw); pw ^= 1; }              // the previous tile's last pass: the M-side blocks are free
       // features straight into slot B: gather_warp's tile layout IS the MN-major swizzle (32-byte chunk ^ (row & 3))
@@ -1152,7 +1154,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
       // ================================ E warps: N side + one Fourier chunk per e-pass ================================
       const float *gubase = a.gu_buf + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
       float g[32], gn[32];
-      load_row32(gubase + pass_block(0) * 4096, g);
+      if (!(a.exp_flags & 16)) load_row32(gubase + pass_block(0) * 4096, g);
 #pragma unroll 1
       for (int ps = 0; ps < NPASS; ++ps) {
         const int st = pcount & 1;
@@ -1163,7 +1165,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         }
         ENS_DBG(ps, 0);
         float ve[32];
-        if (is_epass(ps)) {
+        if (is_epass(ps) && !(a.exp_flags & 8)) {
           const int je = (ps == 2) ? 1 : 2;
 #pragma unroll
           for (int k = 0; k < 32; ++k)
@@ -1180,7 +1182,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // the next block's row, in flight during the barrier and the passes that reuse this one
-        if (ps + 1 < NPASS && pass_block(ps + 1) != pass_block(ps)) load_row32(gubase + pass_block(ps + 1) * 4096, gn);
+        if (ps + 1 < NPASS && pass_block(ps + 1) != pass_block(ps) && !(a.exp_flags & 16)) load_row32(gubase + pass_block(ps + 1) * 4096, gn);
         pend[st] = true;
         ENS_DBG(ps, 3);
         tc_fence_before();
@@ -1192,15 +1194,16 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
       // ================================ H warps: M side + output-layer sums ================================
       const float *rbase = a.save_r + (((int64_t)DEC * a.n_tiles + tile) * 5) * 4096 + pl * 32;
       float c[32], rn[32];
-      if (TAIL) load_row32(rbase + 4 * 4096, rn);                 // r_4: in flight during the gather
+      const bool skip_pro = (a.exp_flags & 32) != 0;
+      if (TAIL && !(a.exp_flags & 16)) load_row32(rbase + 4 * 4096, rn);                 // r_4: in flight during the gather
       const Vox vc = make_vox(pn, a.sc.dims[CLEVEL]);
       const int st0 = pcount & 1;
       float *sM0 = base + st0 * 24576;
       wait_stage(st0);                                            // pass 0's stage: its slot B takes the gather directly
       float *tileB = sM0 + 4096 + w4 * 1024;
       __syncwarp();
-      gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
-      if (TAIL) {
+      if (!skip_pro) gather_warp<32>(a.sc.grid[CLEVEL], a.sc.dims[CLEVEL], vc, tileB, 0);
+      if (TAIL && !skip_pro) {
 #pragma unroll
         for (int o = 0; o < NO; ++o) {
           float t[32];
@@ -1212,9 +1215,9 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
           for (int off = 16; off > 0; off >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, off);
           dbo[o] += sg;
         }
-        load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0
+        if (!(a.exp_flags & 16)) load_row32(rbase + 3 * 4096, rn);                         // r_3: slot A of pass 0
       }
-      {
+      if (!skip_pro) {
         float *lrow = sM0 + 3 * 4096 + w4 * 1024 + lane * 32;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -1248,7 +1251,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
           //   slot A:  r3  r2  e0     e2*    r1  r0  e0   e1        (* = staged by the E warps)
           //   slot B:  c   c   e1*    .      c   .   .    e2*       (c: both stages hold the features)
           const int ja = (ps == 2 || ps == 6) ? 0 : (ps == 7 ? 1 : -1);
-          if (ja >= 0) {
+          if (ja >= 0 && !(a.exp_flags & 8)) {
 #pragma unroll
             for (int k = 0; k < 32; ++k)
               va[k] = fast_sin(fmaf(p32[2], sB[2 * EMBP + 32 * ja + k], fmaf(p32[1], sB[EMBP + 32 * ja + k], p32[0] * sB[32 * ja + k])));
@@ -1259,7 +1262,7 @@ __device__ __forceinline__ void wgrad_tc_body(const BwdTcArgs &a, float *smem_ra
           // the next block pass's slot A (r_{i-2}) is fetched while this pass is staged
           int nxt = -1;
           if (ps + 1 < NPASS) nxt = (ps + 1 == 1) ? 3 : (ps + 1 == 4 ? 2 : (ps + 1 == 5 ? 1 : -1));
-          if (nxt >= 1) load_row32(rbase + (nxt - 1) * 4096, rn);
+          if (nxt >= 1 && !(a.exp_flags & 16)) load_row32(rbase + (nxt - 1) * 4096, rn);
         }
         ENS_DBG(ps, 1);
         wait_stage(st);
